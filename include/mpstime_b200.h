@@ -1,0 +1,169 @@
+/*
+ * mpstime_b200.h -- C ABI of libmpstime_b200.so: the B200-native (sm_100a) implementation of the
+ * MPSTime.jl hot path (fitMPS two-site sweep, classify, MPS_impute).
+ *
+ * The reference (hugopstackhouse/MPSTime.jl) is pure Julia and has no FFI today; these entry
+ * points are what a Julia shim would `ccall` at the seams named next to each function
+ * (paths relative to the reference's src/).  INTEGRATION.md shows the Julia side.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative MPST_E_* code otherwise; the message is
+ *    available from mpst_last_error(ctx).  No exception crosses the boundary.
+ *  - all pointer arguments are caller-owned HOST memory, Float64 / Int64, column-major exactly as
+ *    Julia lays arrays out.  Device memory is owned by the opaque context.
+ *  - a context is bound to one CUDA device and is not re-entrant (one Julia task at a time).
+ *  - sites are 0-based in this ABI (Julia site j  <->  j-1 here).
+ *  - core layout on the wire: dims (chi_left, d, chi_right[, C]) column-major, i.e.
+ *    idx = a + chi_left*(s + d*(b + chi_right*c)); the class axis C is present only on the one
+ *    core that carries the label index "f(x)" (utils.jl:342-354 find_label).
+ *  - bond tensor layout: the reference's `BondTensor = Matrix` (D x C), column c flattened with
+ *    s_l fastest: idx = s_l + d*(a + chi_l*(s_r + d*b))  (Training/loss_functions.jl:193-262).
+ */
+#ifndef MPSTIME_B200_H
+#define MPSTIME_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mpst_ctx mpst_ctx;
+
+enum {
+    MPST_OK = 0,
+    MPST_E_INVALID = -1,   /* bad argument / wrong call order */
+    MPST_E_CUDA = -2,      /* CUDA runtime error */
+    MPST_E_NCCL = -3,      /* NCCL error or libnccl not loadable */
+    MPST_E_NUMERIC = -4,   /* non-finite loss, SVD did not converge */
+    MPST_E_UNSUPPORTED = -5
+};
+
+/* Encodings/bases.jl: data-independent real/complex bases (basis_structs.jl:101-283) */
+enum {
+    MPST_BASIS_LEGENDRE_NO_NORM = 0, /* bases.jl:77-92, norm=false (default encoding, options.jl:111) */
+    MPST_BASIS_LEGENDRE_NORM = 1,    /* bases.jl:86-89 */
+    MPST_BASIS_FOURIER = 2,          /* bases.jl:23-42   (complex: out is re,im interleaved) */
+    MPST_BASIS_STOUDENMIRE = 3,      /* bases.jl:13-20   (complex, d = 2) */
+    MPST_BASIS_SAHAND = 4,           /* bases.jl:53-74   (complex, d even) */
+    MPST_BASIS_UNIFORM = 5,          /* bases.jl:2-5 */
+    MPST_BASIS_PRECOMPUTED = 100     /* caller passes phi (data-driven / custom bases) */
+};
+
+enum { MPST_LOSS_KLD = 0, MPST_LOSS_MSE = 1 };     /* loss_functions.jl:322-432 / 561-619 */
+enum { MPST_OPT_TSGO = 0, MPST_OPT_GD = 1 };       /* loss_functions.jl:59-86 / 27-57 */
+enum { MPST_IMPUTE_MEDIAN = 0, MPST_IMPUTE_MEAN = 1, MPST_IMPUTE_MODE = 2, MPST_IMPUTE_ITS = 3 };
+
+/* Mirrors the MPSOptions fields the sweep reads (Structs/options.jl:106-134). */
+typedef struct mpst_train_opts {
+    int32_t loss_kind;        /* loss_grad  :KLD | :MSE                         */
+    int32_t opt_kind;         /* bbopt      :TSGO | :GD                         */
+    int32_t train_sep;        /* train_classes_separately (KLD only)            */
+    int32_t update_iters;     /* update_iters                                   */
+    int32_t rescale_before;   /* rescale[1]                                     */
+    int32_t rescale_after;    /* rescale[2]                                     */
+    int32_t chi_max;          /* chi_max                                        */
+    int32_t reserved;
+    double eta;               /* eta                                            */
+    double cutoff;            /* cutoff (relative, sum of discarded sigma^2)    */
+} mpst_train_opts;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+int mpst_version(void);
+int mpst_create(mpst_ctx** out, int device_id);
+/* model without a training set (classify / impute with cores passed in): T sites, C classes. */
+int mpst_model_init(mpst_ctx* ctx, int T, int C, int d, int chi_max, int basis_id);
+int mpst_destroy(mpst_ctx* ctx);
+const char* mpst_last_error(mpst_ctx* ctx);
+
+/* ---- multi-GPU plumbing (one process per GPU; the only collective is the per-bond gradient
+ *      all-reduce).  The 128-byte id comes from rank 0 and is broadcast by the host
+ *      language (Distributed.jl / torch.distributed). ------------------------------------- */
+int mpst_comm_unique_id(void* id128);
+int mpst_comm_init(mpst_ctx* ctx, const void* id128, int rank, int world);
+
+/* ---- K1: basis encoding.  Replaces encode_TS -> Basis.encode (Encodings/encodings.jl:18-27,
+ *      bases.jl:13-92).  x: n values already in the encoding range; out: d x n column-major
+ *      (2 x d x n for complex bases). ---------------------------------------------------- */
+int mpst_encode(mpst_ctx* ctx, int basis_id, int d, const double* x, int64_t n, double* out);
+
+/* ---- training set.  Replaces the PState / EncodedTimeSeriesSet / PCache containers
+ *      (Structs/structs.jl:2-33) for the 4-arg fitMPS seam (RealRealHighDimension.jl:587).
+ *      Samples MUST be sorted by class (asserted at :624); class_counts = class_distribution
+ *      (encodings.jl:151-152).  X: T x N column-major (X_train_scaled, series are columns).
+ *      n_global / counts_global: totals over all ranks (== local values on one GPU). ------- */
+int mpst_train_load_x(mpst_ctx* ctx, const double* X, int64_t N, int T, const int64_t* class_counts,
+                      int C, int basis_id, int d, int chi_max, int64_t n_global,
+                      const int64_t* counts_global);
+/* phi: d x T x N column-major (pstate[j][s] of sample i at s + d*(j + T*i)). */
+int mpst_train_load_phi(mpst_ctx* ctx, const double* phi, int64_t N, int T,
+                        const int64_t* class_counts, int C, int d, int chi_max, int64_t n_global,
+                        const int64_t* counts_global);
+
+/* ---- MPS cores in / out (dense-ified ITensors; generate_startingMPS stays on the host,
+ *      RealRealHighDimension.jl:1-41). --------------------------------------------------- */
+int mpst_set_core(mpst_ctx* ctx, int site, const double* data, int chi_l, int chi_r, int has_label);
+int mpst_get_core_dims(mpst_ctx* ctx, int site, int* chi_l, int* chi_r, int* has_label);
+int mpst_get_core(mpst_ctx* ctx, int site, double* out);
+
+/* ---- K6 x (T-1): construct_caches (RealRealHighDimension.jl:45-103). -------------------- */
+int mpst_build_env(mpst_ctx* ctx, int going_left);
+
+/* ---- one bond: flatten_bt -> apply_update -> decomposeBT -> update_caches!
+ *      (RealRealHighDimension.jl:733-762 / 777-801).  lid = left site of the bond (0-based).
+ *      loss_out / gradnorm_out: loss and ||grad||_F of the first optimiser iteration. -------- */
+int mpst_bond_step(mpst_ctx* ctx, int lid, int going_left, const mpst_train_opts* opts,
+                   double* loss_out, double* gradnorm_out, int* chi_new_out);
+
+/* ---- the sweep loop of fitMPS(W, train, test, opts) (RealRealHighDimension.jl:726-852):
+ *      builds LE, runs nsweeps x (backward + forward) half-sweeps, then normalize!(W).
+ *      Optional per-bond outputs have nsweeps*2*(T-1) entries (NULL to skip). ---------------- */
+int mpst_sweep(mpst_ctx* ctx, const mpst_train_opts* opts, int nsweeps, double* per_bond_loss,
+               double* per_bond_gradnorm, int32_t* per_bond_chi);
+
+/* ---- K7: contract_mps / classify / MSE_loss_acc (summary.jl:4-136).  X: T x n column-major in
+ *      the encoding range (basis from the loaded training set) or phi (d x T x n) when the
+ *      context was loaded with precomputed phi.  yhat: C x n column-major; argmax: n (0-based
+ *      class index, first maximum of |yhat|^2). ------------------------------------------- */
+int mpst_overlaps(mpst_ctx* ctx, const double* X_or_phi, int64_t n, double* yhat, int64_t* argmax);
+
+/* ---- K8: MPS_impute batch (Imputation/imputation.jl:264-410 get_predictions ->
+ *      MPS_methods.jl:42-180 precondition + impute_at! -> sampling_utils.jl:64-316).
+ *      Uses the class_idx slice of the context's current MPS (expand_label_index,
+ *      utils.jl:356-370).  X: T x n scaled series with missing entries already filled
+ *      (imputation.jl:290-291); missing: T x n bytes (1 = impute); xgrid: G grid points
+ *      (imputation.jl:90); uniforms: K_max x n_traj x n draws for ITS (NULL otherwise);
+ *      out: T x n_traj x n; max_jump < 0 disables the mode jump filter. ------------------- */
+int mpst_impute_batch(mpst_ctx* ctx, int class_idx, const double* X, const uint8_t* missing,
+                      int64_t n, int method, const double* xgrid, int G, const double* uniforms,
+                      int n_traj, double max_jump, double* out);
+
+/* ---- test / benchmark entry: teacher-forced K2 in isolation on caller-provided operands
+ *      (Loss_Grad_KLD / Loss_Grad_MSE, loss_functions.jl:322-432, 561-619).
+ *      B: D x C; L: chi_l x N; R: chi_r x N; xl, xr: d x N (all column-major, i.e. one sample per
+ *      column).  grad_out: D x C.  yhat_out: C x N (NULL to skip; KLD fills own-class only). - */
+int mpst_bond_loss_grad(mpst_ctx* ctx, const double* B, const double* L, const double* R,
+                        const double* xl, const double* xr, int64_t N, int d, int chi_l, int chi_r,
+                        const int64_t* class_counts, int C, int loss_kind, int train_sep,
+                        double* loss_out, double* grad_out, double* yhat_out);
+
+/* ---- test entry: K5 in isolation (decomposeBT, RealRealHighDimension.jl:146-203).
+ *      B: D x C bond tensor; returns the two new cores in the wire layout
+ *      (core_l: chi_l x d x chi_new [x C if !going_left... see DESIGN.md]), sigma: chi_new. --- */
+int mpst_bond_split(mpst_ctx* ctx, const double* B, int d, int chi_l, int chi_r, int C,
+                    int going_left, int chi_max, double cutoff, int* chi_new, double* core_l,
+                    double* core_r, double* sigma);
+
+/* ---- timing hooks for bench.py: device time (ms, CUDA events on the context's stream) spent in
+ *      each kernel family since the last reset, and launch counts. ------------------------ */
+enum { MPST_T_ENCODE = 0, MPST_T_FLATTEN, MPST_T_FWD, MPST_T_GRAD, MPST_T_UPDATE, MPST_T_SVD,
+       MPST_T_ENV, MPST_T_ALLREDUCE, MPST_T_IMPUTE, MPST_T_COUNT };
+int mpst_profile_enable(mpst_ctx* ctx, int on);
+int mpst_profile_get(mpst_ctx* ctx, double* ms /*MPST_T_COUNT*/, int64_t* launches /*MPST_T_COUNT*/);
+int mpst_profile_reset(mpst_ctx* ctx);
+int64_t mpst_launch_count(mpst_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPSTIME_B200_H */

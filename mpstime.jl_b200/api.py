@@ -1,0 +1,357 @@
+"""Host-side mirror of the reference's public interface for the hot path:
+    MPSOptions / fitMPS / classify / init_imputation_problem / MPS_impute / MPSClassifier
+(reference src/Structs/options.jl, src/Training/RealRealHighDimension.jl:383-890, src/summary.jl:116-177,
+src/Imputation/imputation.jl:48-563, src/MLJIntegration/MLJ_integration.jl).  Julia is not present in
+this image, so this Python layer plays the role of the Julia shim: same names,
+argument meaning and error behaviour; every numeric step of the path goes through the C ABI."""
+from dataclasses import dataclass, field, replace
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import dist as _dist
+from .core import Context, MPSTError, make_opts, BASIS_IDS
+from .preprocess import (encoding_range, generate_starting_mps, invert_test_transform, sort_by_class,
+                         transform_test_data, transform_train_data)
+
+_ENC = {"legendre_no_norm": "legendre_no_norm", "legendre": "legendre_no_norm", "legendre_norm": "legendre_norm",
+        "uniform": "uniform", "fourier": "fourier", "stoudenmire": "stoudenmire", "sahand": "sahand"}
+
+
+@dataclass
+class MPSOptions:
+    """Same 27 fields and defaults as the reference's MPSOptions (Structs/options.jl:106-134)."""
+    verbosity: int = 1
+    nsweeps: int = 10
+    chi_max: int = 25
+    eta: float = 0.01
+    d: int = 5
+    encoding: str = "Legendre_No_Norm"
+    projected_basis: bool = False
+    aux_basis_dim: int = 2
+    cutoff: float = 1e-10
+    update_iters: int = 1
+    dtype: type = np.float64
+    loss_grad: str = "KLD"
+    bbopt: str = "TSGO"
+    track_cost: bool = False
+    rescale: Tuple[bool, bool] = (False, True)
+    train_classes_separately: bool = False
+    encode_classes_separately: bool = False
+    return_encoding_meta_info: bool = False
+    minmax: bool = True
+    exit_early: bool = False
+    sigmoid_transform: bool = True
+    init_rng: int = 1234
+    chi_init: int = 4
+    log_level: int = 3
+    data_bounds: Tuple[float, float] = (0.0, 1.0)
+    use_legacy_ITensor: bool = False
+    svd_alg: str = "divide_and_conquer"
+
+    def _check(self):
+        enc = str(self.encoding).lower().lstrip(":")
+        if enc not in _ENC:
+            raise ValueError(f"encoding {self.encoding!r}: only the data-independent bases run on the device "
+                             "(Legendre, Legendre_No_Norm, Legendre_Norm, Uniform for training; "
+                             "Fourier/Stoudenmire/Sahand for mpst_encode)")
+        if enc in ("fourier", "stoudenmire", "sahand"):
+            # loss_functions.jl:343 keeps yhat in a Ref{Float64}: the array path is real-only
+            raise ValueError("complex encodings cannot be trained on the array path (reference: InexactError)")
+        if str(self.bbopt).upper().lstrip(":") not in ("TSGO", "GD"):
+            # loss_functions.jl:166-170
+            raise ValueError("Optim/OptimKit based solvers currently unimplemented for this version, "
+                             "set 'use_legacy_ITensor=true' in MPSOptions to enable")
+        if str(self.loss_grad).upper().lstrip(":") not in ("KLD", "MSE"):
+            raise ValueError("loss_grad must be :KLD or :MSE on the array path")
+        if self.use_legacy_ITensor:
+            raise ValueError("use_legacy_ITensor=true selects the reference's own ITensor trainer; not this backend")
+        return _ENC[enc]
+
+
+@dataclass
+class EncodedTimeSeriesSet:
+    """Structs/structs.jl:25-33: here the (class-sorted) scaled series instead of per-sample PStates."""
+    X_scaled: np.ndarray            # (T, N) in the encoding range, class-sorted
+    original_data: np.ndarray       # (N, T) raw, class-sorted
+    labels: np.ndarray              # (N,) sorted labels
+    class_distribution: np.ndarray  # counts per sorted class
+
+
+@dataclass
+class TrainedMPS:
+    """Structs/options.jl:398-427: (mps, opts, train_data)."""
+    mps: list                       # cores, python shapes (chi_l, d, chi_r[, C])
+    opts: MPSOptions
+    train_data: EncodedTimeSeriesSet
+    classes: np.ndarray = None
+
+
+_CTX = {}
+
+
+def _context(device=None):
+    if device is None:
+        device = _default_device()
+    if device not in _CTX:
+        _CTX[device] = Context(device)
+    return _CTX[device]
+
+
+def _default_device():
+    import os
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def _train_opts(opts):
+    return make_opts(loss=str(opts.loss_grad).lstrip(":"), bbopt=str(opts.bbopt).lstrip(":"),
+                     train_sep=opts.train_classes_separately, update_iters=opts.update_iters, rescale=opts.rescale,
+                     chi_max=opts.chi_max, eta=opts.eta, cutoff=opts.cutoff)
+
+
+def _eval_set(ctx, X_scaled, label_idx, C):
+    """MSE_loss_acc(_conf) (summary.jl:33-114) from device overlaps."""
+    yh, am = ctx.overlaps(X_TxN=X_scaled)
+    n = yh.shape[0]
+    onehot = np.zeros_like(yh)
+    onehot[np.arange(n), label_idx] = 1.0
+    mse = float(np.mean(0.5 * np.sum((yh - onehot) ** 2, axis=1)))
+    kld = float(np.mean(-np.log(yh[np.arange(n), label_idx] ** 2)))
+    pred = np.argmax(np.abs(yh), axis=1)
+    acc = float(np.mean(pred == label_idx))
+    conf = np.zeros((C, C), dtype=np.int64)
+    np.add.at(conf, (label_idx, pred), 1)
+    return mse, kld, acc, conf
+
+
+def fitMPS(X_train, y_train=None, X_test=None, y_test=None, opts: Optional[MPSOptions] = None, W=None,
+           device=None):
+    """fitMPS(X_train, y_train, X_test, y_test, opts) -> (TrainedMPS, info, test_states)
+    (RealRealHighDimension.jl:383-562 down to the sweep loop :587-890).  X_*: (N, T) rows are series.
+    `W`: optional starting cores (label on the last site), else generate_starting_mps(opts.init_rng)."""
+    opts = opts or MPSOptions()
+    enc = opts._check()
+    X_train = np.asarray(X_train, dtype=np.float64)
+    N, T = X_train.shape
+    y_train = np.zeros(N, dtype=np.int64) if y_train is None else np.asarray(y_train)
+    if not np.issubdtype(y_train.dtype, np.integer):
+        raise ValueError("Classes must be integers")                       # :484
+    has_test = X_test is not None and np.size(X_test) > 0
+    Xs_train, norms = transform_train_data(X_train.T, opts)                # :445
+    Xs_sorted, Xo_sorted, ys, _, classes, counts = sort_by_class(Xs_train, X_train, y_train)
+    a, b = encoding_range(enc)
+    if not np.all((a <= Xs_sorted) & (Xs_sorted <= b)):
+        raise ValueError(f"Data must be rescaled between {a} and {b} before a {opts.encoding} encoding.")
+    C = len(classes)
+    class_keys = {c: i for i, c in enumerate(classes)}
+    train_states = EncodedTimeSeriesSet(Xs_sorted, Xo_sorted, ys, counts)
+    test_states = None
+    if has_test:
+        X_test = np.asarray(X_test, dtype=np.float64)
+        y_test = np.asarray(y_test)
+        if len(set(np.unique(y_test)) - set(classes)):
+            raise ValueError("Test set has classes not present in the training set, this is currently unsupported.")
+        Xs_test, _ = transform_test_data(X_test.T, norms, opts)
+        Xt_sorted, Xto_sorted, yts, _, _, tcounts = sort_by_class(Xs_test, X_test, y_test)
+        test_states = EncodedTimeSeriesSet(Xt_sorted, Xto_sorted, yts, tcounts)
+
+    ctx = _context(device)
+    rank, world = _dist.rank_world()
+    if world > 1:
+        _dist.init_comm(ctx)
+        X_local, counts_local, _ = _dist.shard_samples(Xs_sorted, counts, rank, world)
+    else:
+        X_local, counts_local = Xs_sorted, counts
+    ctx.train_load_x(X_local, counts_local, opts.d, opts.chi_max, basis=enc, n_global=N, counts_global=counts)
+    cores0 = W if W is not None else generate_starting_mps(opts.chi_init, T, opts.d, C, seed=opts.init_rng)
+    ctx.set_cores(cores0)
+
+    info = {"train_loss": [], "train_acc": [], "test_loss": [], "time_taken": [], "train_KL_div": []}
+    if has_test:
+        info.update({"test_acc": [], "test_KL_div": [], "test_conf": []})
+    tr_idx = np.array([class_keys[v] for v in ys])
+    te_idx = np.array([class_keys[v] for v in test_states.labels]) if has_test else None
+
+    def log(elapsed):
+        if opts.log_level <= 0:
+            return None
+        mse, kld, acc, _ = _eval_set(ctx, Xs_sorted, tr_idx, C)
+        info["train_loss"].append(mse); info["train_acc"].append(acc)
+        info["time_taken"].append(elapsed); info["train_KL_div"].append(kld)
+        if has_test:
+            mse_t, kld_t, acc_t, conf = _eval_set(ctx, test_states.X_scaled, te_idx, C)
+            info["test_loss"].append(mse_t); info["test_acc"].append(acc_t)
+            info["test_KL_div"].append(kld_t); info["test_conf"].append(conf)
+        if opts.verbosity > -1:
+            print(f"Training KL Div. {kld} | Training acc. {acc}.")
+        return acc
+
+    import time
+    log(0.0)                                                                # :657-689
+    topts = _train_opts(opts)
+    ctx.build_env(True)                                                     # :631
+    for it in range(opts.nsweeps):                                          # :726
+        t0 = time.time()
+        for j in range(T - 2, -1, -1):                                      # :731
+            ctx.bond_step_quiet(j, True, topts)
+        for j in range(T - 1):                                              # :776
+            ctx.bond_step_quiet(j, False, topts)
+        acc = log(time.time() - t0)                                         # :813-845
+        if opts.exit_early and acc == 1.0:                                  # :847-849
+            break
+    cores = _normalize(ctx.get_cores())                                     # :852
+    ctx.set_cores(cores)
+    log(float("nan"))                                                       # :854-885
+    mps = TrainedMPS(cores, replace(opts), train_states, classes)
+    return mps, info, test_states
+
+
+def _normalize(cores):
+    """normalize!(W) (RealRealHighDimension.jl:852): unit norm, scale spread over all cores."""
+    E = np.ones((1, 1, 1))
+    for A in cores:
+        if A.ndim == 4:
+            E = np.einsum("ab,asmc,bsnc->mnc", E[:, :, 0], A, A)
+        else:
+            E = np.einsum("abc,asm,bsn->mnc", E, A, A)
+    z = np.exp(0.5 * np.log(float(E[0, 0, :].sum())) / len(cores))
+    return [A / z for A in cores]
+
+
+def _load_model(ctx, mps: TrainedMPS):
+    enc = mps.opts._check()
+    T = len(mps.mps)
+    C = [A for A in mps.mps if A.ndim == 4][0].shape[3]
+    chi = max(max(A.shape[0], A.shape[2]) for A in mps.mps)
+    ctx.model_init(T, C, mps.opts.d, max(chi, 1), basis=enc)
+    ctx.set_cores(mps.mps)
+    return enc, T, C
+
+
+def classify(mps: TrainedMPS, X_test, device=None):
+    """classify(mps, X_test) -> predicted labels (summary.jl:155-177 -> :116-136): re-derive the train
+    normalisation from mps.train_data.original_data, scale the test set with it, argmax_c |yhat_c|^2."""
+    X_test = np.asarray(X_test, dtype=np.float64)
+    ctx = _context(device)
+    _load_model(ctx, mps)
+    _, norms = transform_train_data(mps.train_data.original_data.T, mps.opts)     # :159-160
+    Xs, _ = transform_test_data(X_test.T, norms, mps.opts)
+    _, am = ctx.overlaps(X_TxN=Xs)
+    return np.asarray(mps.classes)[am]
+
+
+# ------------------------------------------------------------------------------------------------
+# imputation (Imputation/imputation.jl)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class ImputationProblem:
+    """imputation.jl:10-20."""
+    mps: TrainedMPS
+    X_train: np.ndarray
+    y_train: np.ndarray
+    X_test: np.ndarray
+    y_test: np.ndarray
+    opts: MPSOptions
+    xvals: np.ndarray
+    class_map: dict
+    norms: object = None
+    train_mean: float = 0.0
+
+
+def make_grid(enc_range, dx):
+    """collect(range(a, b; step=dx)) (imputation.jl:90), correctly rounded like Julia's ranges."""
+    a, b = enc_range
+    G = int(np.floor((b - a) / dx + 1e-9)) + 1
+    inv = round(1.0 / dx)
+    if abs(inv * dx - 1.0) < 1e-12 and float(a * inv).is_integer():
+        return (a * inv + np.arange(G)) / inv
+    return a + np.arange(G) * dx
+
+
+def init_imputation_problem(mps: TrainedMPS, X_test, y_test=None, dx=1e-4, guess_range=None, verbosity=1):
+    """init_imputation_problem(mps, X_test, y_test) (imputation.jl:143-190 -> 48-123)."""
+    opts = mps.opts
+    enc = opts._check()
+    X_test = np.asarray(X_test, dtype=np.float64)
+    y_test = np.zeros(X_test.shape[0], dtype=np.int64) if y_test is None else np.asarray(y_test)
+    X_train = mps.train_data.original_data
+    y_train = mps.train_data.labels
+    rng_ = guess_range or encoding_range(enc)
+    xvals = make_grid(rng_, dx)
+    _, norms = transform_train_data(X_train, opts)          # hoisted out of get_predictions (:287)
+    class_map = {c: i for i, c in enumerate(sorted(np.unique(y_train)))}
+    return ImputationProblem(mps, X_train, y_train, X_test, y_test, opts, xvals, class_map, norms,
+                             float(np.mean(X_train)))
+
+
+def get_predictions_batch(imp: ImputationProblem, cls, instances, missing_sites_list, method="median",
+                          invert_transform=True, rseed=1, num_trajectories=1, max_jump=None, uniforms=None,
+                          device=None):
+    """Batched get_predictions (imputation.jl:264-410): instances are indices into the test series of
+    class `cls`; missing_sites_list[k] are the 0-based sites to impute in instance k.
+    Returns (ts (n, n_traj, T), target (n, T))."""
+    ctx = _context(device)
+    _load_model(ctx, imp.mps)
+    opts = imp.opts
+    cl_inds = np.nonzero(imp.y_test == cls)[0]
+    n = len(instances)
+    T = imp.X_test.shape[1]
+    raw = imp.X_test[cl_inds[np.asarray(instances)]]                       # (n, T)
+    filled = raw.copy()
+    mask = np.zeros((n, T), dtype=np.uint8)
+    for k, ms in enumerate(missing_sites_list):
+        filled[k, list(ms)] = imp.train_mean                               # :290
+        mask[k, list(ms)] = 1
+    Xs, oob = transform_test_data(filled.T, imp.norms, opts)               # :291
+    Kmax = int(mask.sum(axis=1).max()) if n else 0
+    if method == "ITS" and uniforms is None:
+        # the reference draws rand(MersenneTwister(rseed)) site by site (MPS_methods.jl:324); callers
+        # needing Julia's stream pass `uniforms` drawn in Julia
+        rs = np.random.RandomState(rseed)
+        uniforms = rs.random_sample((n, num_trajectories, Kmax))
+    out = ctx.impute_batch(imp.class_map[cls], Xs, mask.T, imp.xvals, method=method, uniforms=uniforms,
+                           n_traj=num_trajectories if method == "ITS" else 1,
+                           max_jump=-1.0 if max_jump is None else float(max_jump))
+    if invert_transform:                                                   # :337-394
+        res = np.empty_like(out)
+        for tr in range(out.shape[1]):
+            res[:, tr, :] = invert_test_transform(out[:, tr, :].T, oob, imp.norms, opts).T
+        return res, raw
+    full, _ = transform_test_data(raw.T, imp.norms, opts)
+    return out, full.T
+
+
+def MPS_impute(imp: ImputationProblem, cls, instance, missing_sites, method="median", **kw):
+    """MPS_impute(imp, class, instance, missing_sites, method) (imputation.jl:467-563) without the
+    plotting / kNN-baseline extras: returns (imputed_ts list, pred_err, target, stats)."""
+    ts, target = get_predictions_batch(imp, cls, [instance], [missing_sites], method=method, **kw)
+    ts = [ts[0, t] for t in range(ts.shape[1])]
+    ms = list(missing_sites)
+    stats = [{"MAE": float(np.mean(np.abs(t[ms] - target[0][ms]))),
+              "MAPE": float(np.mean(np.abs((t[ms] - target[0][ms]) / target[0][ms])))} for t in ts]
+    return ts, [None for _ in ts], target[0], stats
+
+
+class MPSClassifier:
+    """MLJ `MPSClassifier` (MLJIntegration/MLJ_integration.jl:2-62): same hyper-parameter fields and
+    defaults; fit/predict route to fitMPS/classify."""
+
+    def __init__(self, nsweeps=5, chi_max=15, eta=0.01, d=2, encoding="Legendre_No_Norm", projected_basis=False,
+                 aux_basis_dim=2, cutoff=1e-10, update_iters=1, loss_grad="KLD", bbopt="TSGO", rescale=(False, True),
+                 train_classes_separately=False, encode_classes_separately=False, minmax=True, exit_early=True,
+                 sigmoid_transform=True, init_rng=1234, chi_init=4, reformat_verbosity=-1):
+        self.__dict__.update({k: v for k, v in locals().items() if k != "self"})
+        self.fitresult = None
+
+    def _opts(self):
+        f = dict(self.__dict__)
+        f.pop("fitresult")
+        f.pop("reformat_verbosity")
+        return MPSOptions(verbosity=-1, log_level=0, **f)
+
+    def fit(self, X, y):
+        self.fitresult, _, _ = fitMPS(X, y, opts=self._opts())
+        return self
+
+    def predict(self, X):
+        return classify(self.fitresult, X)

@@ -1,0 +1,863 @@
+// C ABI of libmpstime_b200.so (see include/mpstime_b200.h) and the host-side sweep driver that
+// replaces the loop of fitMPS(W, train, test, opts) (reference
+// Training/RealRealHighDimension.jl:587-890).  All heavy work is in the CUDA kernels of this
+// directory; nothing here falls back to the CPU.
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "mpst_common.cuh"
+
+// ---- kernel launchers defined in the other translation units ---------------------------------
+int launch_rowdot_q(mpst_ctx* c, const double* Z, int64_t ldz, const double* xr, const double* R,
+                    int64_t row_begin, int64_t row_end, int d, int chi_r, double* yhat);
+int launch_rowdot(mpst_ctx* c, const double* A, int64_t lda, const double* Bm, int64_t ldb, int64_t row_begin,
+                  int64_t row_end, int n, double* yhat);
+int launch_loss_w(mpst_ctx* c, int loss_kind, const int64_t* class_off_dev, const double* denom_dev,
+                  double* loss_out_dev);
+int launch_final_sum(mpst_ctx* c, const double* red, int n, double* out_dev);
+int launch_scale_const(mpst_ctx* c, double* v, int64_t n, double f);
+int launch_transpose(mpst_ctx* c, const double* in, double* out, int64_t rows, int64_t cols, int64_t ldo);
+int launch_fill(mpst_ctx* c, double* v, int64_t n, double val);
+int launch_argmax(mpst_ctx* c, const double* yhat, int64_t Npad, int64_t n, int C, double* out_yhat, int64_t* out_arg);
+int launch_bond_grad(mpst_ctx* c, const double* xl, const double* xr, const double* L, const double* R, int d,
+                     int chi_l, int chi_r, const int64_t* cls_begin, const int64_t* cls_end, int ncls, double* G);
+int svd_split_device(mpst_ctx* c, const double* B, int Dl, int Dr, int C, int going_left, int chi_max,
+                     double cutoff, const double* norm2_dev, double* label_core, double* ortho_core,
+                     int* chi_new, double* sigma_host, int* sweeps_out);
+
+// ---- small helpers ---------------------------------------------------------------------------
+int ensure_buf(mpst_ctx* c, double** p, size_t* cap, size_t need) {
+    if (need <= *cap && *p) return MPST_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    size_t n = need + need / 8 + 256;
+    CUDA_TRY(c, cudaMalloc(p, n * sizeof(double)));
+    *cap = n;
+    return MPST_OK;
+}
+
+void prof_begin(mpst_ctx* c, int kind) {
+    if (!c->prof) return;
+    cudaEvent_t e0, e1;
+    if (c->evpool.size() >= 2) {
+        e0 = c->evpool.back(); c->evpool.pop_back();
+        e1 = c->evpool.back(); c->evpool.pop_back();
+    } else {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+    }
+    cudaEventRecord(e0, c->stream);
+    c->pending.push_back({kind, {e0, e1}});
+}
+void prof_end(mpst_ctx* c, int kind) {
+    if (!c->prof) return;
+    for (int i = (int)c->pending.size() - 1; i >= 0; i--)
+        if (c->pending[i].first == kind) {
+            cudaEventRecord(c->pending[i].second.second, c->stream);
+            c->prof_n[kind]++;
+            return;
+        }
+}
+static void prof_drain(mpst_ctx* c) {
+    if (c->pending.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& p : c->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.second.first, p.second.second) == cudaSuccess) c->prof_ms[p.first] += ms;
+        c->evpool.push_back(p.second.first);
+        c->evpool.push_back(p.second.second);
+    }
+    c->pending.clear();
+}
+
+struct ProfScope {
+    mpst_ctx* c; int k;
+    ProfScope(mpst_ctx* c_, int k_) : c(c_), k(k_) { prof_begin(c, k); }
+    ~ProfScope() { prof_end(c, k); if (c->prof && c->pending.size() > 4096) prof_drain(c); }
+};
+
+static CoreView view_of(const Core& k, int d) {
+    CoreView v;
+    v.p = k.dev;
+    v.ss = 1;
+    if (k.orient == ORIENT_LEFT) { v.sa = d; v.sb = (long)d * k.chi_l; }
+    else { v.sb = d; v.sa = (long)d * k.chi_r; }
+    v.sc = k.has_label ? (long)d * k.chi_l * k.chi_r : 0;
+    return v;
+}
+
+static int core_reserve(mpst_ctx* c, Core& k, size_t need) {
+    if (need <= k.cap && k.dev) return MPST_OK;
+    double* nd = nullptr;
+    CUDA_TRY(c, cudaMalloc(&nd, need * sizeof(double)));
+    if (k.dev) cudaFree(k.dev);
+    k.dev = nd;
+    k.cap = need;
+    return MPST_OK;
+}
+
+static int core_orient(mpst_ctx* c, int site, int want) {
+    Core& k = c->cores[site];
+    if (k.orient == want) return MPST_OK;
+    const int d = c->d, C = k.has_label ? c->C : 1;
+    const size_t n = (size_t)d * k.chi_l * k.chi_r * C;
+    TRY(ensure_buf(c, &c->tmp, &c->tmpcap, n));
+    CoreView s = view_of(k, d);
+    Core t = k;
+    t.orient = want;
+    t.dev = c->tmp;
+    CoreView dv = view_of(t, d);
+    const long csz = (long)d * k.chi_l * k.chi_r;
+    TRY(launch_permute_core(c, k.dev, c->tmp, d, k.chi_l, k.chi_r, C, s.ss, s.sa, s.sb, csz, dv.ss, dv.sa, dv.sb, csz));
+    CUDA_TRY(c, cudaMemcpyAsync(k.dev, c->tmp, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    k.orient = want;
+    return MPST_OK;
+}
+
+static size_t slot_stride(const mpst_ctx* c) { return (size_t)c->Npad * c->chi_max; }
+static double* slot_ptr(mpst_ctx* c, int site) { return c->env + (size_t)site * slot_stride(c); }
+
+static void free_training(mpst_ctx* c) {
+    auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
+    fr(c->X); fr(c->PHI); fr(c->phi_l); fr(c->phi_r); fr(c->env); fr(c->ones); fr(c->yhat); fr(c->w);
+    for (auto& k : c->cores) if (k.dev) cudaFree(k.dev);
+    c->cores.clear();
+    c->env_chi.clear();
+    c->N = c->Npad = 0;
+    c->T = 0;
+    c->meta_key = 0;
+}
+
+// ---- NCCL through dlopen (no link-time dependency; prefers the copy already in the process) ---
+namespace {
+struct NcclId { char internal[128]; };
+typedef int (*fn_getid)(NcclId*);
+typedef int (*fn_init)(void**, int, NcclId, int);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_destroy)(void*);
+typedef const char* (*fn_errstr)(int);
+struct NcclApi {
+    void* h = nullptr;
+    fn_getid getid = nullptr; fn_init init = nullptr; fn_allreduce allreduce = nullptr;
+    fn_destroy destroy = nullptr; fn_errstr errstr = nullptr;
+} g_nccl;
+bool nccl_load() {
+    if (g_nccl.h) return true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+    if (!h) return false;
+    g_nccl.getid = (fn_getid)dlsym(h, "ncclGetUniqueId");
+    g_nccl.init = (fn_init)dlsym(h, "ncclCommInitRank");
+    g_nccl.allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
+    g_nccl.destroy = (fn_destroy)dlsym(h, "ncclCommDestroy");
+    g_nccl.errstr = (fn_errstr)dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.getid || !g_nccl.init || !g_nccl.allreduce) return false;
+    g_nccl.h = h;
+    return true;
+}
+}  // namespace
+
+static int allreduce_sum(mpst_ctx* c, double* buf, size_t count) {
+    if (c->world <= 1) return MPST_OK;
+    ProfScope ps(c, MPST_T_ALLREDUCE);
+    int r = g_nccl.allreduce(buf, buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl_comm, c->stream);
+    if (r != 0) { c->err = std::string("ncclAllReduce: ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return MPST_E_NCCL; }
+    return MPST_OK;
+}
+
+// =============================================================================================
+extern "C" {
+
+int mpst_version(void) { return 100; }
+
+int mpst_create(mpst_ctx** out, int device_id) {
+    if (!out) return MPST_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return MPST_E_CUDA;   // no CPU fallback
+    if (device_id < 0 || device_id >= ndev) return MPST_E_INVALID;
+    mpst_ctx* c = new mpst_ctx();
+    c->device = device_id;
+    if (cudaSetDevice(device_id) != cudaSuccess) { delete c; return MPST_E_CUDA; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device_id);
+    if (prop.major < 10) { delete c; return MPST_E_UNSUPPORTED; }               // sm_100a only
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MPST_E_CUDA; }
+    cudaMalloc(&c->scal, 32 * sizeof(double));
+    cudaMemset(c->scal, 0, 32 * sizeof(double));
+    cudaMallocHost(&c->hscal, 32 * sizeof(double));
+    cudaMalloc(&c->meta, 256 * sizeof(double));
+    cudaMallocHost(&c->hmeta, 256 * sizeof(double));
+    cudaMalloc(&c->iscal, 16 * sizeof(int));
+    cudaMallocHost(&c->hiscal, 16 * sizeof(int));
+    const size_t maxn = (size_t)MPST_MAX_D * MPST_MAX_CHI + 64;
+    cudaMalloc(&c->colnorm, 2 * maxn * sizeof(double));
+    cudaMalloc(&c->perm, maxn * sizeof(int));
+    *out = c;
+    return MPST_OK;
+}
+
+int mpst_destroy(mpst_ctx* c) {
+    if (!c) return MPST_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    prof_drain(c);
+    for (auto e : c->evpool) cudaEventDestroy(e);
+    free_training(c);
+    auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
+    fr(c->B); fr(c->G); fr(c->Z); fr(c->part); fr(c->red); fr(c->scal); fr(c->S); fr(c->gpart); fr(c->wbuf);
+    fr(c->colnorm); fr(c->tmp); fr(c->meta);
+    if (c->hmeta) cudaFreeHost(c->hmeta);
+    if (c->perm) cudaFree(c->perm);
+    if (c->iscal) cudaFree(c->iscal);
+    if (c->hscal) cudaFreeHost(c->hscal);
+    if (c->hiscal) cudaFreeHost(c->hiscal);
+    if (c->segs) { cudaFree(c->segs); cudaFree(c->cta_ptr); cudaFree(c->tile_slot); }
+    if (c->hsegs) { cudaFreeHost(c->hsegs); cudaFreeHost(c->hcta_ptr); cudaFreeHost(c->htile_slot); }
+    if (c->nccl_comm && g_nccl.destroy) g_nccl.destroy(c->nccl_comm);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return MPST_OK;
+}
+
+const char* mpst_last_error(mpst_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int mpst_comm_unique_id(void* id128) {
+    if (!id128) return MPST_E_INVALID;
+    if (!nccl_load()) return MPST_E_NCCL;
+    NcclId id;
+    if (g_nccl.getid(&id) != 0) return MPST_E_NCCL;
+    memcpy(id128, &id, 128);
+    return MPST_OK;
+}
+
+int mpst_comm_init(mpst_ctx* c, const void* id128, int rank, int world) {
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return MPST_E_INVALID;
+    c->rank = rank;
+    c->world = world;
+    if (world == 1) return MPST_OK;
+    if (!nccl_load()) { c->err = "libnccl.so.2 not loadable"; return MPST_E_NCCL; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    NcclId id;
+    memcpy(&id, id128, 128);
+    int r = g_nccl.init(&c->nccl_comm, world, id, rank);
+    if (r != 0) { c->err = std::string("ncclCommInitRank: ") + (g_nccl.errstr ? g_nccl.errstr(r) : "?"); return MPST_E_NCCL; }
+    return MPST_OK;
+}
+
+int mpst_encode(mpst_ctx* c, int basis_id, int d, const double* x, int64_t n, double* out) {
+    if (!c || !x || !out || n < 0) return MPST_E_INVALID;
+    if (n == 0) return MPST_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const bool cplx = basis_id >= MPST_BASIS_FOURIER && basis_id <= MPST_BASIS_SAHAND;
+    const int width = cplx ? 2 * d : d;
+    if (basis_id == MPST_BASIS_STOUDENMIRE && d != 2) { c->err = "Stoudenmire encoding needs d = 2"; return MPST_E_INVALID; }
+    if (basis_id == MPST_BASIS_SAHAND && (d & 1)) { c->err = "Sahand encoding needs even d"; return MPST_E_INVALID; }
+    TRY(ensure_buf(c, &c->tmp, &c->tmpcap, (size_t)n * (width + 1)));
+    double* dx = c->tmp;
+    double* dout = c->tmp + n;
+    CUDA_TRY(c, cudaMemcpyAsync(dx, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    {
+        ProfScope ps(c, MPST_T_ENCODE);
+        TRY(launch_encode(c, basis_id, d, dx, n, dout, width));
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(out, dout, (size_t)n * width * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MPST_OK;
+}
+
+static int model_reset(mpst_ctx* c, int T, int C, int d, int chi_max) {
+    if (T < 2 || C < 1 || d < 1 || d > MPST_MAX_D || chi_max < 1 || chi_max > MPST_MAX_CHI) {
+        c->err = "bad model shape (need T>=2, C>=1, 1<=d<=32, 1<=chi_max<=128)";
+        return MPST_E_INVALID;
+    }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    free_training(c);
+    c->T = T; c->C = C; c->d = d; c->chi_max = chi_max;
+    c->env_chi.assign(T, 0);
+    c->cores.assign(T, Core());
+    return MPST_OK;
+}
+
+static int train_common(mpst_ctx* c, int64_t N, int T, const int64_t* class_counts, int C, int d, int chi_max,
+                        int64_t n_global, const int64_t* counts_global) {
+    if (N <= 0) { c->err = "train_load: N must be positive"; return MPST_E_INVALID; }
+    int64_t s = 0;
+    for (int k = 0; k < C; k++) { if (class_counts[k] < 0) return MPST_E_INVALID; s += class_counts[k]; }
+    if (s != N) { c->err = "train_load: class_counts do not sum to N"; return MPST_E_INVALID; }
+    TRY(model_reset(c, T, C, d, chi_max));
+    c->N = N;
+    c->Npad = round_up(N, MPST_TILE) + MPST_TILE;
+    c->Nglobal = n_global > 0 ? n_global : N;
+    c->counts.assign(class_counts, class_counts + C);
+    c->counts_global.assign(counts_global ? counts_global : class_counts, (counts_global ? counts_global : class_counts) + C);
+    c->class_off.assign(C + 1, 0);
+    for (int k = 0; k < C; k++) c->class_off[k + 1] = c->class_off[k] + class_counts[k];
+    CUDA_TRY(c, cudaMalloc(&c->phi_l, sizeof(double) * c->Npad * d));
+    CUDA_TRY(c, cudaMalloc(&c->phi_r, sizeof(double) * c->Npad * d));
+    CUDA_TRY(c, cudaMemsetAsync(c->phi_l, 0, sizeof(double) * c->Npad * d, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->phi_r, 0, sizeof(double) * c->Npad * d, c->stream));
+    CUDA_TRY(c, cudaMalloc(&c->env, sizeof(double) * slot_stride(c) * T));
+    CUDA_TRY(c, cudaMemsetAsync(c->env, 0, sizeof(double) * slot_stride(c) * T, c->stream));
+    CUDA_TRY(c, cudaMalloc(&c->ones, sizeof(double) * c->Npad));
+    TRY(launch_fill(c, c->ones, c->Npad, 1.0));
+    CUDA_TRY(c, cudaMalloc(&c->yhat, sizeof(double) * c->Npad * C));
+    CUDA_TRY(c, cudaMalloc(&c->w, sizeof(double) * c->Npad * C));
+    CUDA_TRY(c, cudaMemsetAsync(c->yhat, 0, sizeof(double) * c->Npad * C, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->w, 0, sizeof(double) * c->Npad * C, c->stream));
+    return MPST_OK;
+}
+
+int mpst_model_init(mpst_ctx* c, int T, int C, int d, int chi_max, int basis_id) {
+    if (!c) return MPST_E_INVALID;
+    TRY(model_reset(c, T, C, d, chi_max));
+    c->basis = basis_id;
+    c->have_phi = basis_id == MPST_BASIS_PRECOMPUTED;
+    return MPST_OK;
+}
+
+int mpst_train_load_x(mpst_ctx* c, const double* X, int64_t N, int T, const int64_t* class_counts, int C,
+                      int basis_id, int d, int chi_max, int64_t n_global, const int64_t* counts_global) {
+    if (!c || !X || !class_counts) return MPST_E_INVALID;
+    if (basis_id != MPST_BASIS_LEGENDRE_NO_NORM && basis_id != MPST_BASIS_LEGENDRE_NORM && basis_id != MPST_BASIS_UNIFORM) {
+        // loss_functions.jl keeps yhat in a Ref{Float64}: the array training path is real-only
+        c->err = "train_load_x: the training path is real-valued; complex bases are not supported";
+        return MPST_E_UNSUPPORTED;
+    }
+    TRY(train_common(c, N, T, class_counts, C, d, chi_max, n_global, counts_global));
+    c->basis = basis_id;
+    c->have_phi = false;
+    CUDA_TRY(c, cudaMalloc(&c->X, sizeof(double) * c->Npad * T));
+    CUDA_TRY(c, cudaMemsetAsync(c->X, 0, sizeof(double) * c->Npad * T, c->stream));
+    // host: T x N column-major == row-major [N][T]; device: site-major [T][Npad]
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)(64 << 20) / (8 * (int64_t)T));
+    TRY(ensure_buf(c, &c->tmp, &c->tmpcap, (size_t)std::min<int64_t>(chunk, N) * T));
+    for (int64_t i0 = 0; i0 < N; i0 += chunk) {
+        const int64_t nn = std::min<int64_t>(chunk, N - i0);
+        CUDA_TRY(c, cudaMemcpyAsync(c->tmp, X + i0 * T, sizeof(double) * nn * T, cudaMemcpyHostToDevice, c->stream));
+        TRY(launch_transpose(c, c->tmp, c->X + i0, nn, T, c->Npad));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    return MPST_OK;
+}
+
+int mpst_train_load_phi(mpst_ctx* c, const double* phi, int64_t N, int T, const int64_t* class_counts, int C, int d,
+                        int chi_max, int64_t n_global, const int64_t* counts_global) {
+    if (!c || !phi || !class_counts) return MPST_E_INVALID;
+    TRY(train_common(c, N, T, class_counts, C, d, chi_max, n_global, counts_global));
+    c->basis = MPST_BASIS_PRECOMPUTED;
+    c->have_phi = true;
+    CUDA_TRY(c, cudaMalloc(&c->PHI, sizeof(double) * c->Npad * d * T));
+    CUDA_TRY(c, cudaMemsetAsync(c->PHI, 0, sizeof(double) * c->Npad * d * T, c->stream));
+    // host [N][T][d] -> device [T][Npad][d]: one strided 2-D copy per site
+    for (int j = 0; j < T; j++)
+        CUDA_TRY(c, cudaMemcpy2DAsync(c->PHI + (size_t)j * c->Npad * d, sizeof(double) * d, phi + (size_t)j * d,
+                                      sizeof(double) * d * T, sizeof(double) * d, N, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MPST_OK;
+}
+
+int mpst_set_core(mpst_ctx* c, int site, const double* data, int chi_l, int chi_r, int has_label) {
+    if (!c || !data || c->T == 0 || site < 0 || site >= c->T || chi_l < 1 || chi_r < 1) return MPST_E_INVALID;
+    if (chi_l > c->chi_max && chi_l > 1) { c->err = "set_core: chi_l exceeds chi_max"; return MPST_E_INVALID; }
+    if (chi_r > c->chi_max && chi_r > 1) { c->err = "set_core: chi_r exceeds chi_max"; return MPST_E_INVALID; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int d = c->d, C = has_label ? c->C : 1;
+    const size_t n = (size_t)d * chi_l * chi_r * C;
+    Core& k = c->cores[site];
+    const size_t cap = (size_t)d * c->chi_max * c->chi_max * c->C;     // room for any later update
+    TRY(core_reserve(c, k, std::max(cap, n)));
+    k.chi_l = chi_l; k.chi_r = chi_r; k.has_label = has_label ? 1 : 0; k.orient = ORIENT_LEFT;
+    TRY(ensure_buf(c, &c->tmp, &c->tmpcap, n));
+    CUDA_TRY(c, cudaMemcpyAsync(c->tmp, data, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // wire: a + chi_l*(s + d*(b + chi_r*c))  ->  LEFT: s + d*(a + chi_l*b) + d*chi_l*chi_r*c
+    TRY(launch_permute_core(c, c->tmp, k.dev, d, chi_l, chi_r, C, chi_l, 1, (long)chi_l * d, (long)chi_l * d * chi_r, 1, d,
+                            (long)d * chi_l, (long)d * chi_l * chi_r));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MPST_OK;
+}
+
+int mpst_get_core_dims(mpst_ctx* c, int site, int* chi_l, int* chi_r, int* has_label) {
+    if (!c || site < 0 || site >= c->T || !c->cores[site].dev) return MPST_E_INVALID;
+    if (chi_l) *chi_l = c->cores[site].chi_l;
+    if (chi_r) *chi_r = c->cores[site].chi_r;
+    if (has_label) *has_label = c->cores[site].has_label;
+    return MPST_OK;
+}
+
+int mpst_get_core(mpst_ctx* c, int site, double* out) {
+    if (!c || !out || site < 0 || site >= c->T || !c->cores[site].dev) return MPST_E_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    Core& k = c->cores[site];
+    const int d = c->d, C = k.has_label ? c->C : 1;
+    const size_t n = (size_t)d * k.chi_l * k.chi_r * C;
+    TRY(ensure_buf(c, &c->tmp, &c->tmpcap, n));
+    CoreView s = view_of(k, d);
+    TRY(launch_permute_core(c, k.dev, c->tmp, d, k.chi_l, k.chi_r, C, s.ss, s.sa, s.sb, (long)d * k.chi_l * k.chi_r,
+                            k.chi_l, 1, (long)k.chi_l * d, (long)k.chi_l * d * k.chi_r));
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->tmp, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MPST_OK;
+}
+
+// encoded vectors of one site for all local samples -> dst ([Npad][d]); phi mode returns a view
+static int site_phi(mpst_ctx* c, int site, double* dst, const double** out) {
+    if (c->have_phi) { *out = c->PHI + (size_t)site * c->Npad * c->d; return MPST_OK; }
+    ProfScope ps(c, MPST_T_ENCODE);
+    TRY(launch_encode(c, c->basis, c->d, c->X + (size_t)site * c->Npad, c->N, dst, c->d));
+    *out = dst;
+    return MPST_OK;
+}
+
+int mpst_build_env(mpst_ctx* c, int going_left) {
+    if (!c || c->T == 0) return MPST_E_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int T = c->T, d = c->d;
+    for (int j = 0; j < T; j++) if (!c->cores[j].dev) { c->err = "build_env: cores not set"; return MPST_E_INVALID; }
+    int pos = -1;
+    for (int j = 0; j < T; j++) if (c->cores[j].has_label) pos = j;
+    if (pos < 0) { c->err = "build_env: no label core"; return MPST_E_INVALID; }
+    // The reference builds LE[1..T-1] with the label on the last site (:65-77) resp. RE[T..2] with it on
+    // the first (:80-95); here the chain simply stops at the label core, which covers both and lets a
+    // caller position the environments for any bond (teacher-forced tests).
+    if (going_left) {
+        for (int j = 0; j < pos; j++) {
+            Core& k = c->cores[j];
+            TRY(core_orient(c, j, ORIENT_LEFT));
+            const double* ph;
+            TRY(site_phi(c, j, c->phi_l, &ph));
+            const double* E = j > 0 ? slot_ptr(c, j - 1) : c->ones;
+            ProfScope ps(c, MPST_T_ENV);
+            TRY(launch_krao_gemm(c, ph, E, k.dev, slot_ptr(c, j), c->N, d, k.chi_l, k.chi_r, (int64_t)d * k.chi_l, k.chi_r));
+            c->env_chi[j] = k.chi_r;
+        }
+    } else {
+        for (int j = T - 1; j > pos; j--) {
+            Core& k = c->cores[j];
+            TRY(core_orient(c, j, ORIENT_RIGHT));
+            const double* ph;
+            TRY(site_phi(c, j, c->phi_r, &ph));
+            const double* E = j < T - 1 ? slot_ptr(c, j + 1) : c->ones;
+            ProfScope ps(c, MPST_T_ENV);
+            TRY(launch_krao_gemm(c, ph, E, k.dev, slot_ptr(c, j), c->N, d, k.chi_r, k.chi_l, (int64_t)d * k.chi_r, k.chi_l));
+            c->env_chi[j] = k.chi_l;
+        }
+    }
+    return MPST_OK;
+}
+
+// ---- loss + gradient on device operands ([Npad][.] row-major, B/G as [C][Dl*Dr]) -------------
+static int loss_grad_device(mpst_ctx* c, const double* phl, const double* phr, const double* L, const double* R,
+                            int chi_l, int chi_r, const double* B, double* G, int loss_kind, int train_sep,
+                            double* loss_dev, int64_t* coff_dev, double* denom_dev) {
+    const int d = c->d, C = c->C;
+    const int Dl = d * chi_l, Dr = d * chi_r;
+    const size_t D = (size_t)Dl * Dr;
+    // forward: yhat[c][i] = <B_c, phi~_i>  (dense: Z = P * B_c in row blocks, then the Q-weighted row sum)
+    {
+        ProfScope ps(c, MPST_T_FWD);
+        const int64_t SB = std::max<int64_t>(MPST_TILE, ((int64_t)(96 << 20) / (8 * (int64_t)Dr)) / MPST_TILE * MPST_TILE);
+        TRY(ensure_buf(c, &c->Z, &c->Zcap, (size_t)(SB + 2 * MPST_TILE) * Dr));
+        for (int cls = 0; cls < C; cls++) {
+            const int64_t b0 = loss_kind == MPST_LOSS_KLD ? c->class_off[cls] : 0;
+            const int64_t b1 = loss_kind == MPST_LOSS_KLD ? c->class_off[cls + 1] : c->N;
+            for (int64_t rb = b0; rb < b1;) {
+                // keep blocks on the 128-row tile grid so each tile is computed once
+                int64_t re = std::min<int64_t>(b1, (rb / MPST_TILE) * MPST_TILE + SB);
+                double* Zv = c->Z - rb * (int64_t)Dr;                  // absolute-row view of the scratch
+                TRY(launch_krao_gemm_rows(c, phl, L, B + cls * D, Zv, rb, re, d, chi_l, Dr, Dl, Dr));
+                TRY(launch_rowdot_q(c, c->Z, Dr, phr, R, rb, re, d, chi_r, c->yhat + (size_t)cls * c->Npad));
+                rb = re;
+            }
+        }
+        TRY(launch_loss_w(c, loss_kind, coff_dev, denom_dev, loss_dev));
+    }
+    {
+        ProfScope ps(c, MPST_T_GRAD);
+        std::vector<int64_t> cb(C), ce(C);
+        for (int cls = 0; cls < C; cls++) {
+            cb[cls] = loss_kind == MPST_LOSS_KLD ? c->class_off[cls] : 0;
+            ce[cls] = loss_kind == MPST_LOSS_KLD ? c->class_off[cls + 1] : c->N;
+        }
+        TRY(launch_bond_grad(c, phl, phr, L, R, d, chi_l, chi_r, cb.data(), ce.data(), C, G));
+    }
+    (void)train_sep;
+    return MPST_OK;
+}
+
+// class offsets and loss normalisers on the device (denominators use the GLOBAL counts so that
+// sharded ranks sum to the reference's 1/N resp. 1/N_c, loss_functions.jl:367,371,424-425)
+static int upload_class_meta(mpst_ctx* c, int loss_kind, int train_sep, int64_t** coff_dev, double** denom_dev) {
+    const int C = c->C;
+    if (C > 64) { c->err = "more than 64 classes unsupported"; return MPST_E_UNSUPPORTED; }
+    *coff_dev = reinterpret_cast<int64_t*>(c->meta);
+    *denom_dev = c->meta + 128;
+    const int key = 1 + loss_kind * 2 + (train_sep ? 1 : 0);
+    if (c->meta_key == key) return MPST_OK;
+    int64_t* hoff = reinterpret_cast<int64_t*>(c->hmeta);
+    for (int k = 0; k < 256; k++) c->hmeta[k] = 0.0;
+    for (int k = 0; k <= C; k++) hoff[k] = c->class_off[k];
+    for (int k = 0; k < C; k++)
+        c->hmeta[128 + k] = (loss_kind == MPST_LOSS_KLD && train_sep) ? (double)c->counts_global[k] : (double)c->Nglobal;
+    CUDA_TRY(c, cudaMemcpyAsync(c->meta, c->hmeta, 256 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->meta_key = key;
+    return MPST_OK;
+}
+
+int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* o, double* loss_out,
+                   double* gradnorm_out, int* chi_new_out) {
+    if (!c || !o || c->T == 0 || lid < 0 || lid >= c->T - 1) return MPST_E_INVALID;
+    if (o->update_iters < 1 || o->chi_max < 1 || o->chi_max > c->chi_max) { c->err = "bond_step: bad options"; return MPST_E_INVALID; }
+    if (o->loss_kind == MPST_LOSS_MSE && o->train_sep) { c->err = "MSE has no train_classes_separately variant (loss_functions.jl:561)"; return MPST_E_UNSUPPORTED; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int l = lid, r = lid + 1, d = c->d, C = c->C, T = c->T;
+    Core& kl = c->cores[l];
+    Core& kr = c->cores[r];
+    if (!kl.dev || !kr.dev) { c->err = "bond_step: cores not set"; return MPST_E_INVALID; }
+    if (kl.has_label + kr.has_label != 1) { c->err = "bond_step: the label index must be on one of the two bond sites"; return MPST_E_INVALID; }
+    if (kl.chi_r != kr.chi_l) { c->err = "bond_step: link dimension mismatch"; return MPST_E_INVALID; }
+    const int chi_l = kl.chi_l, chi_m = kl.chi_r, chi_r = kr.chi_r;
+    if (l > 0 && c->env_chi[l - 1] != chi_l) { c->err = "bond_step: left environment missing/stale"; return MPST_E_INVALID; }
+    if (r < T - 1 && c->env_chi[r + 1] != chi_r) { c->err = "bond_step: right environment missing/stale"; return MPST_E_INVALID; }
+    const int Dl = d * chi_l, Dr = d * chi_r;
+    const size_t D = (size_t)Dl * Dr;
+    if (D * C + 64 > c->Dcap) {
+        if (c->B) cudaFree(c->B);
+        if (c->G) cudaFree(c->G);
+        c->Dcap = (size_t)d * d * c->chi_max * c->chi_max * C + 64;
+        c->Dcap = std::max(c->Dcap, D * C + 64);
+        CUDA_TRY(c, cudaMalloc(&c->B, c->Dcap * sizeof(double)));
+        CUDA_TRY(c, cudaMalloc(&c->G, c->Dcap * sizeof(double)));
+    }
+    const double *phl, *phr;
+    TRY(site_phi(c, l, c->phi_l, &phl));
+    TRY(site_phi(c, r, c->phi_r, &phr));
+    const double* L = l > 0 ? slot_ptr(c, l - 1) : c->ones;
+    const double* R = r < T - 1 ? slot_ptr(c, r + 1) : c->ones;
+    {
+        ProfScope ps(c, MPST_T_FLATTEN);
+        TRY(launch_flatten(c, view_of(kl, d), view_of(kr, d), d, chi_l, chi_m, chi_r, C, c->B));
+    }
+    int64_t* coff_dev;
+    double* denom_dev;
+    TRY(upload_class_meta(c, o->loss_kind, o->train_sep, &coff_dev, &denom_dev));
+    double* s_loss = c->G + D * C;          // contiguous with G: one all-reduce covers both
+    double* s_gn2 = c->scal + 1;
+    double* s_bn2 = c->scal + 2;
+    if (o->rescale_before) {                // loss_functions.jl:109-111
+        ProfScope ps(c, MPST_T_UPDATE);
+        TRY(launch_sumsq(c, c->B, D * C, s_bn2));
+        TRY(launch_scale_dev(c, c->B, D * C, s_bn2));
+    }
+    for (int it = 0; it < o->update_iters; it++) {
+        TRY(loss_grad_device(c, phl, phr, L, R, chi_l, chi_r, c->B, c->G, o->loss_kind, o->train_sep, s_loss, coff_dev, denom_dev));
+        TRY(allreduce_sum(c, c->G, D * C + 1));
+        ProfScope ps(c, MPST_T_UPDATE);
+        TRY(launch_sumsq(c, c->G, D * C, s_gn2));
+        if (it == 0 && (loss_out || gradnorm_out)) {
+            CUDA_TRY(c, cudaMemcpyAsync(c->hscal, s_loss, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaMemcpyAsync(c->hscal + 1, s_gn2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            if (loss_out) *loss_out = c->hscal[0];
+            if (gradnorm_out) *gradnorm_out = sqrt(c->hscal[1]);
+            if (!std::isfinite(c->hscal[0]) || !std::isfinite(c->hscal[1])) {
+                c->err = "bond_step: non-finite loss or gradient (yhat hit zero?)";
+                return MPST_E_NUMERIC;
+            }
+        }
+        TRY(launch_axpy(c, c->B, c->G, D * C, s_gn2, o->eta, o->opt_kind == MPST_OPT_TSGO));
+    }
+    const double* norm2_dev = nullptr;
+    if (o->rescale_after) {                 // loss_functions.jl:177-179 (scaling fused into the SVD load)
+        ProfScope ps(c, MPST_T_UPDATE);
+        TRY(launch_sumsq(c, c->B, D * C, s_bn2));
+        norm2_dev = s_bn2;
+    }
+    int chi_new = 0;
+    {
+        ProfScope ps(c, MPST_T_SVD);
+        Core& klabel = going_left ? kl : kr;
+        Core& kortho = going_left ? kr : kl;
+        const size_t cap = (size_t)d * c->chi_max * c->chi_max * C;
+        TRY(core_reserve(c, klabel, cap));
+        TRY(core_reserve(c, kortho, cap));
+        TRY(svd_split_device(c, c->B, Dl, Dr, C, going_left, o->chi_max, o->cutoff, norm2_dev, klabel.dev, kortho.dev,
+                             &chi_new, nullptr, nullptr));
+    }
+    if (going_left) {       // W[l] <- U*S with the label (LEFT), W[r] <- V (RIGHT)   (:161-176)
+        kl.chi_r = chi_new; kl.has_label = 1; kl.orient = ORIENT_LEFT;
+        kr.chi_l = chi_new; kr.has_label = 0; kr.orient = ORIENT_RIGHT;
+        ProfScope ps(c, MPST_T_ENV);     // update_caches! :124-131
+        TRY(launch_krao_gemm(c, phr, R, kr.dev, slot_ptr(c, r), c->N, d, chi_r, chi_new, Dr, chi_new));
+        c->env_chi[r] = chi_new;
+    } else {                // W[l] <- U (LEFT), W[r] <- V*S with the label (RIGHT)   (:177-196)
+        kl.chi_r = chi_new; kl.has_label = 0; kl.orient = ORIENT_LEFT;
+        kr.chi_l = chi_new; kr.has_label = 1; kr.orient = ORIENT_RIGHT;
+        ProfScope ps(c, MPST_T_ENV);     // update_caches! :132-141
+        TRY(launch_krao_gemm(c, phl, L, kl.dev, slot_ptr(c, l), c->N, d, chi_l, chi_new, Dl, chi_new));
+        c->env_chi[l] = chi_new;
+    }
+    if (chi_new_out) *chi_new_out = chi_new;
+    return MPST_OK;
+}
+
+int mpst_sweep(mpst_ctx* c, const mpst_train_opts* o, int nsweeps, double* per_bond_loss, double* per_bond_gradnorm,
+               int32_t* per_bond_chi) {
+    if (!c || !o || c->T == 0 || nsweeps < 0) return MPST_E_INVALID;
+    const int T = c->T;
+    if (!c->cores[T - 1].dev || !c->cores[T - 1].has_label) { c->err = "sweep: the label index must start on the last site"; return MPST_E_INVALID; }
+    TRY(mpst_build_env(c, 1));                                        // :631
+    size_t idx = 0;
+    for (int it = 0; it < nsweeps; it++) {
+        for (int pass = 0; pass < 2; pass++) {
+            for (int t = 0; t < T - 1; t++) {
+                const int j = pass == 0 ? T - 2 - t : t;              // backward :731, forward :776
+                double lo = 0, gn = 0;
+                int chi = 0;
+                const bool want = per_bond_loss || per_bond_gradnorm;
+                TRY(mpst_bond_step(c, j, pass == 0, o, want ? &lo : nullptr, want ? &gn : nullptr, &chi));
+                if (per_bond_loss) per_bond_loss[idx] = lo;
+                if (per_bond_gradnorm) per_bond_gradnorm[idx] = gn;
+                if (per_bond_chi) per_bond_chi[idx] = chi;
+                idx++;
+            }
+        }
+    }
+    // normalize!(W) (:852).  After a full sweep the MPS is in canonical form with its centre on the
+    // label core, so <W|W> = ||label core||_F^2; ITensors spreads the scale evenly over all cores.
+    if (nsweeps > 0) {
+        Core& k = c->cores[T - 1];
+        const size_t n = (size_t)c->d * k.chi_l * k.chi_r * c->C;
+        TRY(launch_sumsq(c, k.dev, n, c->scal + 3));
+        CUDA_TRY(c, cudaMemcpyAsync(c->hscal + 3, c->scal + 3, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        const double z = exp(0.5 * log(c->hscal[3]) / T);
+        for (int j = 0; j < T; j++) {
+            Core& q = c->cores[j];
+            TRY(launch_scale_const(c, q.dev, (size_t)c->d * q.chi_l * q.chi_r * (q.has_label ? c->C : 1), 1.0 / z));
+        }
+        // environments no longer match the rescaled cores
+        std::fill(c->env_chi.begin(), c->env_chi.end(), 0);
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MPST_OK;
+}
+
+int mpst_overlaps(mpst_ctx* c, const double* X_or_phi, int64_t n, double* yhat, int64_t* argmax) {
+    if (!c || !X_or_phi || c->T == 0 || n < 0 || (!yhat && !argmax)) return MPST_E_INVALID;
+    if (n == 0) return MPST_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int T = c->T, d = c->d, C = c->C;
+    int pos = -1;
+    for (int j = 0; j < T; j++) {
+        if (!c->cores[j].dev) { c->err = "overlaps: cores not set"; return MPST_E_INVALID; }
+        if (c->cores[j].has_label) pos = j;
+    }
+    if (pos < 0) { c->err = "overlaps: no label core"; return MPST_E_INVALID; }
+    for (int j = 0; j < pos; j++) TRY(core_orient(c, j, ORIENT_LEFT));
+    for (int j = pos + 1; j < T; j++) TRY(core_orient(c, j, ORIENT_RIGHT));
+    TRY(core_orient(c, pos, ORIENT_LEFT));
+    const int chimax = c->chi_max;
+    const int64_t BS = std::min<int64_t>(round_up(n, MPST_TILE), 1 << 16);       // samples per batch
+    const int64_t BP = BS + MPST_TILE;
+    const int width = c->have_phi ? d : 1;
+    // buffers: xin [T][BP][width], phi [BP][d], envA/envB/envR [BP][chimax], Z [BP][chimax*C], y [C][BP], outputs
+    const size_t need = (size_t)T * BP * width + (size_t)BP * d + 3 * (size_t)BP * chimax + (size_t)BP * chimax * C +
+                        (size_t)C * BP + (size_t)BP * C + 2 * BP + 64;
+    double* buf = nullptr;
+    CUDA_TRY(c, cudaMalloc(&buf, need * sizeof(double)));
+    CUDA_TRY(c, cudaMemsetAsync(buf, 0, need * sizeof(double), c->stream));
+    double* xin = buf;
+    double* ph = xin + (size_t)T * BP * width;
+    double* eA = ph + (size_t)BP * d;
+    double* eB = eA + (size_t)BP * chimax;
+    double* eR = eB + (size_t)BP * chimax;
+    double* Z = eR + (size_t)BP * chimax;
+    double* y = Z + (size_t)BP * chimax * C;
+    double* oy = y + (size_t)C * BP;
+    int64_t* oarg = reinterpret_cast<int64_t*>(oy + (size_t)BP * C);
+    double* ones = oy + (size_t)BP * C + BP;
+    if (launch_fill(c, ones, BP, 1.0) != MPST_OK) { cudaFree(buf); return MPST_E_CUDA; }
+    int rc = MPST_OK;
+    auto body = [&]() -> int {
+        for (int64_t i0 = 0; i0 < n; i0 += BS) {
+            const int64_t nn = std::min<int64_t>(BS, n - i0);
+            if (c->have_phi) {
+                for (int j = 0; j < T; j++)
+                    CUDA_TRY(c, cudaMemcpy2DAsync(xin + (size_t)j * BP * d, sizeof(double) * d, X_or_phi + ((size_t)i0 * T + j) * d,
+                                                  sizeof(double) * d * T, sizeof(double) * d, nn, cudaMemcpyHostToDevice, c->stream));
+            } else {
+                TRY(ensure_buf(c, &c->tmp, &c->tmpcap, (size_t)nn * T));
+                CUDA_TRY(c, cudaMemcpyAsync(c->tmp, X_or_phi + (size_t)i0 * T, sizeof(double) * nn * T, cudaMemcpyHostToDevice, c->stream));
+                TRY(launch_transpose(c, c->tmp, xin, nn, T, BP));
+            }
+            auto phi_of = [&](int j, const double** out) -> int {
+                if (c->have_phi) { *out = xin + (size_t)j * BP * d; return MPST_OK; }
+                TRY(launch_encode(c, c->basis, d, xin + (size_t)j * BP, nn, ph, d));
+                *out = ph;
+                return MPST_OK;
+            };
+            ProfScope ps(c, MPST_T_ENV);
+            // left chain up to pos-1
+            const double* E = ones;
+            int chiE = 1;
+            double* cur = eA;
+            double* nxt = eB;
+            for (int j = 0; j < pos; j++) {
+                const Core& k = c->cores[j];
+                const double* p;
+                TRY(phi_of(j, &p));
+                TRY(launch_krao_gemm(c, p, E, k.dev, cur, nn, d, chiE, k.chi_r, (int64_t)d * k.chi_l, k.chi_r));
+                E = cur; chiE = k.chi_r;
+                std::swap(cur, nxt);
+            }
+            const double* LEp = E;
+            const int chiL = chiE;
+            // right chain down to pos+1
+            const double* Er = ones;
+            int chiR = 1;
+            double* rc1 = eR;
+            double* rc2 = (LEp == eA) ? eB : eA;
+            for (int j = T - 1; j > pos; j--) {
+                const Core& k = c->cores[j];
+                const double* p;
+                TRY(phi_of(j, &p));
+                TRY(launch_krao_gemm(c, p, Er, k.dev, rc1, nn, d, chiR, k.chi_l, (int64_t)d * k.chi_r, k.chi_l));
+                Er = rc1; chiR = k.chi_l;
+                std::swap(rc1, rc2);
+            }
+            // label site: Z[i][b + chi_r*c] = sum_{s,a} x[s] LE[a] core[c][s,a,b];  yhat_c = Z_c . RE
+            const Core& kp = c->cores[pos];
+            const double* p;
+            TRY(phi_of(pos, &p));
+            if (chiL != kp.chi_l || chiR != kp.chi_r) { c->err = "overlaps: inconsistent link dimensions"; return MPST_E_INVALID; }
+            TRY(launch_krao_gemm(c, p, LEp, kp.dev, Z, nn, d, chiL, kp.chi_r * C, (int64_t)d * kp.chi_l, (int64_t)kp.chi_r * C));
+            for (int cls = 0; cls < C; cls++)
+                TRY(launch_rowdot(c, Z + (size_t)cls * kp.chi_r, (int64_t)kp.chi_r * C, Er, chiR, 0, nn, kp.chi_r, y + (size_t)cls * BP));
+            TRY(launch_argmax(c, y, BP, nn, C, oy, oarg));
+            if (yhat) CUDA_TRY(c, cudaMemcpyAsync(yhat + (size_t)i0 * C, oy, sizeof(double) * nn * C, cudaMemcpyDeviceToHost, c->stream));
+            if (argmax) CUDA_TRY(c, cudaMemcpyAsync(argmax + i0, oarg, sizeof(int64_t) * nn, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        }
+        return MPST_OK;
+    };
+    rc = body();
+    cudaStreamSynchronize(c->stream);
+    cudaFree(buf);
+    return rc;
+}
+
+int mpst_bond_loss_grad(mpst_ctx* c, const double* B, const double* L, const double* R, const double* xl,
+                        const double* xr, int64_t N, int d, int chi_l, int chi_r, const int64_t* class_counts, int C,
+                        int loss_kind, int train_sep, double* loss_out, double* grad_out, double* yhat_out) {
+    if (!c || !B || !L || !R || !xl || !xr || !class_counts || !loss_out || !grad_out) return MPST_E_INVALID;
+    if (loss_kind == MPST_LOSS_MSE && train_sep) { c->err = "MSE has no train_classes_separately variant"; return MPST_E_UNSUPPORTED; }
+    if (chi_l > MPST_MAX_CHI || chi_r > MPST_MAX_CHI) { c->err = "chi too large"; return MPST_E_UNSUPPORTED; }
+    // stand-alone operands: reuse the training-set containers with T = 2 (invalidates a loaded set)
+    TRY(train_common(c, N, 2, class_counts, C, d, std::max(chi_l, chi_r), N, class_counts));
+    c->have_phi = true;
+    c->basis = MPST_BASIS_PRECOMPUTED;
+    const int Dl = d * chi_l, Dr = d * chi_r;
+    const size_t D = (size_t)Dl * Dr;
+    if (D * C + 64 > c->Dcap) {
+        if (c->B) cudaFree(c->B);
+        if (c->G) cudaFree(c->G);
+        c->Dcap = D * C + 64;
+        CUDA_TRY(c, cudaMalloc(&c->B, c->Dcap * sizeof(double)));
+        CUDA_TRY(c, cudaMalloc(&c->G, c->Dcap * sizeof(double)));
+    }
+    double* dL = slot_ptr(c, 0);
+    double* dR = slot_ptr(c, 1);
+    CUDA_TRY(c, cudaMemcpyAsync(c->B, B, D * C * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(dL, L, sizeof(double) * N * chi_l, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(dR, R, sizeof(double) * N * chi_r, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->phi_l, xl, sizeof(double) * N * d, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->phi_r, xr, sizeof(double) * N * d, cudaMemcpyHostToDevice, c->stream));
+    int64_t* coff_dev;
+    double* denom_dev;
+    TRY(upload_class_meta(c, loss_kind, train_sep, &coff_dev, &denom_dev));
+    double* s_loss = c->G + D * C;
+    TRY(loss_grad_device(c, c->phi_l, c->phi_r, dL, dR, chi_l, chi_r, c->B, c->G, loss_kind, train_sep, s_loss, coff_dev, denom_dev));
+    CUDA_TRY(c, cudaMemcpyAsync(grad_out, c->G, D * C * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->hscal, s_loss, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (yhat_out) {
+        TRY(ensure_buf(c, &c->tmp, &c->tmpcap, (size_t)N * C + N));
+        int64_t* dummy = reinterpret_cast<int64_t*>(c->tmp + (size_t)N * C);
+        TRY(launch_argmax(c, c->yhat, c->Npad, N, C, c->tmp, dummy));
+        CUDA_TRY(c, cudaMemcpyAsync(yhat_out, c->tmp, sizeof(double) * N * C, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *loss_out = c->hscal[0];
+    return MPST_OK;
+}
+
+int mpst_bond_split(mpst_ctx* c, const double* B, int d, int chi_l, int chi_r, int C, int going_left, int chi_max,
+                    double cutoff, int* chi_new, double* core_l, double* core_r, double* sigma) {
+    if (!c || !B || !chi_new || !core_l || !core_r) return MPST_E_INVALID;
+    if (d > MPST_MAX_D || chi_l > MPST_MAX_CHI || chi_r > MPST_MAX_CHI) { c->err = "bond_split: shape too large"; return MPST_E_UNSUPPORTED; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int Dl = d * chi_l, Dr = d * chi_r;
+    const size_t D = (size_t)Dl * Dr;
+    const int n = going_left ? Dr : Dl, m = C * (going_left ? Dl : Dr);
+    const int kmax = std::max(1, std::min(n, chi_max));
+    double *dB = nullptr, *dlab = nullptr, *dort = nullptr;
+    CUDA_TRY(c, cudaMalloc(&dB, D * C * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&dlab, (size_t)m * kmax * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc(&dort, (size_t)n * kmax * sizeof(double)));
+    CUDA_TRY(c, cudaMemcpyAsync(dB, B, D * C * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    int rc = svd_split_device(c, dB, Dl, Dr, C, going_left, chi_max, cutoff, nullptr, dlab, dort, chi_new, sigma, nullptr);
+    if (rc == MPST_OK) {
+        const int k = *chi_new;
+        // device: label core [c][x + Dx*k] (x = s + d*link), ortho core [y + n*k]  ->  wire layouts
+        Core lab, ort;
+        lab.dev = dlab; lab.has_label = 1; ort.dev = dort; ort.has_label = 0;
+        if (going_left) { lab.chi_l = chi_l; lab.chi_r = k; lab.orient = ORIENT_LEFT; ort.chi_l = k; ort.chi_r = chi_r; ort.orient = ORIENT_RIGHT; }
+        else { ort.chi_l = chi_l; ort.chi_r = k; ort.orient = ORIENT_LEFT; lab.chi_l = k; lab.chi_r = chi_r; lab.orient = ORIENT_RIGHT; }
+        Core* pl = going_left ? &lab : &ort;
+        Core* pr = going_left ? &ort : &lab;
+        for (int which = 0; which < 2 && rc == MPST_OK; which++) {
+            Core* k2 = which == 0 ? pl : pr;
+            const int CC = k2->has_label ? C : 1;
+            const size_t nn = (size_t)d * k2->chi_l * k2->chi_r * CC;
+            rc = ensure_buf(c, &c->tmp, &c->tmpcap, nn);
+            if (rc != MPST_OK) break;
+            CoreView s = view_of(*k2, d);
+            rc = launch_permute_core(c, k2->dev, c->tmp, d, k2->chi_l, k2->chi_r, CC, s.ss, s.sa, s.sb, (long)d * k2->chi_l * k2->chi_r,
+                                     k2->chi_l, 1, (long)k2->chi_l * d, (long)k2->chi_l * d * k2->chi_r);
+            if (rc != MPST_OK) break;
+            if (cudaMemcpyAsync(which == 0 ? core_l : core_r, c->tmp, nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = "bond_split: copy back failed"; rc = MPST_E_CUDA; }
+        }
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaFree(dB); cudaFree(dlab); cudaFree(dort);
+    return rc;
+}
+
+int mpst_impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* missing, int64_t n, int method,
+                      const double* xgrid, int G, const double* uniforms, int n_traj, double max_jump, double* out) {
+    if (!c) return MPST_E_INVALID;
+    return impute_batch(c, class_idx, X, missing, n, method, xgrid, G, uniforms, n_traj, max_jump, out);
+}
+
+int mpst_profile_enable(mpst_ctx* c, int on) { if (!c) return MPST_E_INVALID; c->prof = on != 0; return MPST_OK; }
+int mpst_profile_reset(mpst_ctx* c) {
+    if (!c) return MPST_E_INVALID;
+    prof_drain(c);
+    for (int k = 0; k < MPST_T_COUNT; k++) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
+    c->launches = 0;
+    return MPST_OK;
+}
+int mpst_profile_get(mpst_ctx* c, double* ms, int64_t* launches) {
+    if (!c) return MPST_E_INVALID;
+    prof_drain(c);
+    for (int k = 0; k < MPST_T_COUNT; k++) { if (ms) ms[k] = c->prof_ms[k]; if (launches) launches[k] = c->prof_n[k]; }
+    return MPST_OK;
+}
+int64_t mpst_launch_count(mpst_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,267 @@
+// K2 (gradient half): the summed two-site gradient of Loss_Grad_KLD / Loss_Grad_MSE
+// (reference Training/loss_functions.jl:322-432, 561-619; inner loop kron_scaleadd_* :203-262,
+// 435-496):
+//     G_c[p, q] = sum_i w_c[i] * (xl_i (x) L_i)[p] * (xr_i (x) R_i)[q]
+//     p = s_l + d*a   (rows, d*chi_l),   q = s_r + d*b   (cols, d*chi_r)
+// with w_c[i] = -1/(N yhat_i) on the samples of class c (KLD) or (yhat_ic - delta)/N (MSE).
+// The reference forms phi~_i explicitly (D doubles per sample) and does a rank-1 update per
+// sample; here it is one FP64 tensor-core GEMM  G_c = P^T diag(w_c) Q  whose K dimension is the
+// sample index and whose two Khatri-Rao operands are formed in shared memory from the raw
+// per-sample factors (L, R rows and the two encoded site vectors), never in HBM.
+//
+// Schedule: stream-K.  The (class, p-tile, q-tile, 16-sample chunk) space is cut into one
+// contiguous range per CTA (grid = #SMs), so every SM gets the same number of chunks whatever
+// the tile count; a CTA writes one partial tile per (tile, range) segment and a second kernel
+// sums the segments of each tile in a fixed order (deterministic, no atomics).
+// Per chunk the raw factors arrive by 1-D bulk TMA (rows of 16 consecutive samples are contiguous)
+// on a 2-stage mbarrier ring; the 128x16 / 16x128 operand tiles are double buffered.
+#include "mpst_common.cuh"
+#include "dmma.cuh"
+
+namespace {
+constexpr int TP = 128, TQ = 128, KC = 16, LDT = TP + 4;   // pitch == 4 (mod 16): conflict-free
+constexpr int MI = 4, NI = 8;                              // warp tile 32 x 64, warps 4 x 2
+
+struct RawStage {
+    double* L;
+    double* R;
+    double* xl;
+    double* xr;
+    double* w;
+};
+
+__global__ void __launch_bounds__(256, 1)
+bond_grad_kernel(const double* __restrict__ xl, const double* __restrict__ xr,
+                 const double* __restrict__ L, const double* __restrict__ R,
+                 const double* __restrict__ w, int64_t wstride, int d, int chi_l, int chi_r,
+                 const GradSeg* __restrict__ segs, const int* __restrict__ cta_ptr,
+                 double* __restrict__ part) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smraw);          // 2 barriers
+    double* base = reinterpret_cast<double*>(smraw + 16);
+    const int raw_sz = KC * (chi_l + chi_r + 2 * d + 1);
+    double* raw[2] = {base, base + raw_sz};
+    double* Pt = base + 2 * raw_sz;                               // [2][KC][LDT]
+    double* Qt = Pt + 2 * KC * LDT;
+    const int Dl = d * chi_l, Dr = d * chi_r;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wp = warp & 3, wq = warp >> 2;
+    const int fr = lane >> 2, fc = lane & 3;
+    const uint32_t raw_bytes = (uint32_t)(raw_sz * sizeof(double));
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase[2] = {0, 0};
+
+    auto stage_ptrs = [&](int s) {
+        RawStage r;
+        r.L = raw[s];
+        r.R = r.L + KC * chi_l;
+        r.xl = r.R + KC * chi_r;
+        r.xr = r.xl + KC * d;
+        r.w = r.xr + KC * d;
+        return r;
+    };
+    auto issue = [&](int s, int cls, int64_t chunk) {             // one thread
+        RawStage r = stage_ptrs(s);
+        const int64_t i0 = chunk * KC;
+        fence_proxy_async();
+        mbar_expect_tx(&bars[s], raw_bytes);
+        bulk_g2s(r.L, L + i0 * chi_l, (uint32_t)(KC * chi_l * sizeof(double)), &bars[s]);
+        bulk_g2s(r.R, R + i0 * chi_r, (uint32_t)(KC * chi_r * sizeof(double)), &bars[s]);
+        bulk_g2s(r.xl, xl + i0 * d, (uint32_t)(KC * d * sizeof(double)), &bars[s]);
+        bulk_g2s(r.xr, xr + i0 * d, (uint32_t)(KC * d * sizeof(double)), &bars[s]);
+        bulk_g2s(r.w, w + (int64_t)cls * wstride + i0, (uint32_t)(KC * sizeof(double)), &bars[s]);
+    };
+
+    for (int sg = cta_ptr[blockIdx.x]; sg < cta_ptr[blockIdx.x + 1]; sg++) {
+        const GradSeg seg = segs[sg];
+        const int p0 = seg.tp * TP, q0 = seg.tq * TQ;
+        // this thread's column of the P / Q tiles
+        const int pl = tid & 127, ihalf = tid >> 7;
+        const int pp = p0 + pl, qq = q0 + pl;
+        const bool pok = pp < Dl, qok = qq < Dr;
+        const int pa = pok ? pp / d : 0, ps = pok ? pp - pa * d : 0;
+        const int qb = qok ? qq / d : 0, qs = qok ? qq - qb * d : 0;
+
+        auto build = [&](int s, int buf) {
+            RawStage r = stage_ptrs(s);
+            double* P = Pt + buf * KC * LDT;
+            double* Q = Qt + buf * KC * LDT;
+#pragma unroll
+            for (int rr = 0; rr < KC / 2; rr++) {
+                const int i = 2 * rr + ihalf;
+                const double wi = r.w[i];
+                P[i * LDT + pl] = pok ? wi * r.xl[i * d + ps] * r.L[i * chi_l + pa] : 0.0;
+                Q[i * LDT + pl] = qok ? r.xr[i * d + qs] * r.R[i * chi_r + qb] : 0.0;
+            }
+        };
+
+        double acc[MI][NI][2];
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+        const int64_t nch = seg.chunk_end - seg.chunk_begin;
+        // prologue: raw(0), raw(1) in flight; build(0)
+        if (tid == 0) {
+            issue(0, seg.cls, seg.chunk_begin);
+            if (nch > 1) issue(1, seg.cls, seg.chunk_begin + 1);
+        }
+        mbar_wait(&bars[0], phase[0]);
+        phase[0] ^= 1;
+        build(0, 0);
+        __syncthreads();                                           // built[0] visible, raw[0] free
+        if (tid == 0 && nch > 2) issue(0, seg.cls, seg.chunk_begin + 2);
+
+        for (int64_t j = 0; j < nch; j++) {
+            const int cur = (int)(j & 1);
+            if (j + 1 < nch) {                                     // build the next operand tiles
+                const int s = (int)((j + 1) & 1);
+                mbar_wait(&bars[s], phase[s]);
+                phase[s] ^= 1;
+                build(s, cur ^ 1);
+            }
+            const double* Pc = Pt + cur * KC * LDT + fc * LDT + wp * 32 + fr;
+            const double* Qc = Qt + cur * KC * LDT + fc * LDT + wq * 64 + fr;
+#pragma unroll
+            for (int k4 = 0; k4 < KC / 4; k4++) {
+                double a[MI], b[NI];
+#pragma unroll
+                for (int mi = 0; mi < MI; mi++) a[mi] = Pc[k4 * 4 * LDT + mi * 8];
+#pragma unroll
+                for (int ni = 0; ni < NI; ni++) b[ni] = Qc[k4 * 4 * LDT + ni * 8];
+#pragma unroll
+                for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < NI; ni++)
+                        dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+            __syncthreads();                                       // built[cur] consumed, raw[(j+1)&1] free
+            if (tid == 0 && j + 3 < nch) issue((int)((j + 1) & 1), seg.cls, seg.chunk_begin + j + 3);
+        }
+
+        // partial tile: dense TP x TQ, p fastest
+        double* dst = part + (size_t)seg.slot * TP * TQ;
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) {
+                const int p = wp * 32 + mi * 8 + fr;
+                const int q = wq * 64 + ni * 8 + 2 * fc;
+                dst[p + TP * q] = acc[mi][ni][0];
+                dst[p + TP * (q + 1)] = acc[mi][ni][1];
+            }
+        __syncthreads();
+    }
+}
+
+// G[c][p + Dl*q] = sum over the tile's segments, fixed order
+__global__ void __launch_bounds__(256)
+grad_reduce_kernel(const double* __restrict__ part, const int* __restrict__ tile_slot, int ntp, int ntq,
+                   int Dl, int Dr, double* __restrict__ G) {
+    const int tile = blockIdx.x;                                   // cls*ntp*ntq + tp*ntq + tq
+    const int cls = tile / (ntp * ntq);
+    const int rem = tile - cls * ntp * ntq;
+    const int tp = rem / ntq, tq = rem - tp * ntq;
+    const int s0 = tile_slot[tile], s1 = tile_slot[tile + 1];
+    double* Gc = G + (size_t)cls * Dl * Dr;
+    for (int e = threadIdx.x; e < TP * TQ; e += blockDim.x) {
+        const int pl = e % TP, ql = e / TP;
+        const int p = tp * TP + pl, q = tq * TQ + ql;
+        if (p >= Dl || q >= Dr) continue;
+        double s = 0.0;
+        for (int sl = s0; sl < s1; sl++) s += part[(size_t)sl * TP * TQ + e];
+        Gc[(size_t)p + (size_t)Dl * q] = s;
+    }
+}
+}  // namespace
+
+// Host side: build the stream-K table for `ncls` class segments.  cls_begin/cls_end are sample
+// ranges (KLD: the class's own samples; MSE: all samples for every class).
+int launch_bond_grad(mpst_ctx* c, const double* xl, const double* xr, const double* L, const double* R,
+                     int d, int chi_l, int chi_r, const int64_t* cls_begin, const int64_t* cls_end,
+                     int ncls, double* G) {
+    const int Dl = d * chi_l, Dr = d * chi_r;
+    const int ntp = (Dl + TP - 1) / TP, ntq = (Dr + TQ - 1) / TQ;
+    const int ntiles = ncls * ntp * ntq;
+    const int ncta = c->sm_count;
+    // chunks per class
+    std::vector<int64_t> cb(ncls), ce(ncls);
+    int64_t total = 0;
+    for (int k = 0; k < ncls; k++) {
+        cb[k] = cls_begin[k] / KC;
+        ce[k] = (cls_end[k] + KC - 1) / KC;
+        if (cls_end[k] <= cls_begin[k]) ce[k] = cb[k];
+        total += (ce[k] - cb[k]) * ntp * ntq;
+    }
+    const size_t max_segs = (size_t)ntiles + ncta + 2;
+    if (max_segs > c->segcap) {
+        if (c->segs) { cudaFree(c->segs); cudaFree(c->cta_ptr); cudaFree(c->tile_slot); }
+        if (c->hsegs) { cudaFreeHost(c->hsegs); cudaFreeHost(c->hcta_ptr); cudaFreeHost(c->htile_slot); }
+        c->segcap = max_segs * 2;
+        CUDA_TRY(c, cudaMalloc(&c->segs, c->segcap * sizeof(GradSeg)));
+        CUDA_TRY(c, cudaMalloc(&c->cta_ptr, (ncta + 1) * sizeof(int)));
+        CUDA_TRY(c, cudaMalloc(&c->tile_slot, (c->segcap + 1) * sizeof(int)));
+        CUDA_TRY(c, cudaMallocHost(&c->hsegs, c->segcap * sizeof(GradSeg)));
+        CUDA_TRY(c, cudaMallocHost(&c->hcta_ptr, (ncta + 1) * sizeof(int)));
+        CUDA_TRY(c, cudaMallocHost(&c->htile_slot, (c->segcap + 1) * sizeof(int)));
+    }
+    // the pinned tables may still be in flight from the previous bond
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    int nseg = 0;
+    if (total == 0) {
+        CUDA_TRY(c, cudaMemsetAsync(G, 0, sizeof(double) * (size_t)ncls * Dl * Dr, c->stream));
+        return MPST_OK;
+    }
+    // linear work space: tile-major, chunks within the tile
+    int64_t pos = 0;      // global chunk cursor
+    int cta = 0;
+    int64_t cta_end = (total * (cta + 1)) / ncta;
+    c->hcta_ptr[0] = 0;
+    for (int tile = 0; tile < ntiles; tile++) {
+        const int cls = tile / (ntp * ntq);
+        const int rem = tile - cls * ntp * ntq;
+        const int tp = rem / ntq, tq = rem - tp * ntq;
+        c->htile_slot[tile] = nseg;
+        int64_t j = cb[cls];
+        while (j < ce[cls]) {
+            while (pos >= cta_end && cta < ncta - 1) {           // advance to the CTA owning `pos`
+                cta++;
+                c->hcta_ptr[cta] = nseg;
+                cta_end = (total * (cta + 1)) / ncta;
+            }
+            const int64_t take = std::min<int64_t>(ce[cls] - j, cta_end - pos);
+            GradSeg sgm;
+            sgm.cls = cls; sgm.tp = tp; sgm.tq = tq; sgm.slot = nseg;
+            sgm.chunk_begin = j; sgm.chunk_end = j + take;
+            c->hsegs[nseg++] = sgm;
+            j += take;
+            pos += take;
+        }
+    }
+    c->htile_slot[ntiles] = nseg;
+    while (cta < ncta) { cta++; c->hcta_ptr[cta] = nseg; }
+    const size_t need_part = (size_t)nseg * TP * TQ;
+    TRY(ensure_buf(c, &c->part, &c->partcap, need_part));
+    CUDA_TRY(c, cudaMemcpyAsync(c->segs, c->hsegs, nseg * sizeof(GradSeg), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->cta_ptr, c->hcta_ptr, (ncta + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->tile_slot, c->htile_slot, (ntiles + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+
+    const size_t smem = 16 + sizeof(double) * (2 * (size_t)KC * (chi_l + chi_r + 2 * d + 1) + 4 * (size_t)KC * LDT);
+    CUDA_TRY(c, cudaFuncSetAttribute(bond_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bond_grad_kernel<<<ncta, 256, smem, c->stream>>>(xl, xr, L, R, c->w, c->Npad, d, chi_l, chi_r, c->segs,
+                                                    c->cta_ptr, c->part);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    grad_reduce_kernel<<<ntiles, 256, 0, c->stream>>>(c->part, c->tile_slot, ntp, ntq, Dl, Dr, G);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return MPST_OK;
+}

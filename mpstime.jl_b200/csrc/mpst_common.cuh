@@ -1,0 +1,148 @@
+// Shared declarations for libmpstime_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/mpstime_b200.h"
+
+#define MPST_MAX_D 32
+#define MPST_MAX_CHI 128
+#define MPST_TILE 128          // sample padding granularity
+
+// ---------------------------------------------------------------------------------------------
+// device storage of one MPS core.  Two orientations: the link that points towards
+// the bond being optimised is the slowest ("k") index so that the core is directly the weight
+// matrix [p = s + d*env_link][k] of the Khatri-Rao GEMM that updates the environment.
+//   LEFT : idx = s + d*(a + chi_l*b) + d*chi_l*chi_r*c     (site, left link, right link[, class])
+//   RIGHT: idx = s + d*(b + chi_r*a) + d*chi_l*chi_r*c     (site, right link, left link[, class])
+// ---------------------------------------------------------------------------------------------
+enum { ORIENT_LEFT = 0, ORIENT_RIGHT = 1 };
+
+struct Core {
+    double* dev = nullptr;
+    size_t cap = 0;   // doubles allocated
+    int chi_l = 0, chi_r = 0, has_label = 0, orient = ORIENT_LEFT;
+};
+
+struct CoreView {       // strides (in doubles) of (s, a = left link, b = right link, c = class)
+    const double* p;
+    long ss, sa, sb, sc;
+};
+
+struct GradSeg {        // one stream-K segment of the gradient GEMM (host-built, see bond_grad)
+    int cls, tp, tq, slot;
+    int64_t chunk_begin, chunk_end;
+};
+
+struct Timer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+struct mpst_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // training set
+    int64_t N = 0, Npad = 0, Nglobal = 0;
+    int T = 0, d = 0, C = 0, chi_max = 0, basis = 0;
+    bool have_phi = false;
+    std::vector<int64_t> counts, counts_global, class_off;
+    double* X = nullptr;        // [T][Npad]   (x mode)
+    double* PHI = nullptr;      // [T][Npad][d] (phi mode)
+    double* phi_l = nullptr;    // [Npad][d] two-site window
+    double* phi_r = nullptr;
+    double* env = nullptr;      // [T][Npad][chi_max] shared LE/RE slots (SURVEY 7 "cache memory")
+    std::vector<int> env_chi;   // link dim held by each slot
+    double* ones = nullptr;     // [Npad] == 1.0 (dummy boundary environments)
+    std::vector<Core> cores;
+    // bond scratch
+    double* B = nullptr;        // [C][D]
+    double* G = nullptr;        // [C][D] (+1 slot for the loss, contiguous for the all-reduce)
+    size_t Dcap = 0;
+    double* yhat = nullptr;     // [C][Npad]
+    double* w = nullptr;        // [C][Npad]
+    double* Z = nullptr;        // scratch rows x ldz for the dense forward
+    size_t Zcap = 0;
+    double* part = nullptr;     // stream-K partial tiles
+    size_t partcap = 0;
+    double* red = nullptr;      // reduction scratch (doubles)
+    size_t redcap = 0;
+    double* scal = nullptr;     // device scalars [16]
+    double* hscal = nullptr;    // pinned host mirror
+    GradSeg* segs = nullptr;    // device segment table
+    int* cta_ptr = nullptr;
+    int* tile_slot = nullptr;
+    size_t segcap = 0;
+    GradSeg* hsegs = nullptr;   // pinned
+    int* hcta_ptr = nullptr;
+    int* htile_slot = nullptr;
+    // jacobi workspace
+    double* S = nullptr;        // (m+n) x npad column-major
+    size_t Scap = 0;
+    double* gpart = nullptr;
+    size_t gpartcap = 0;
+    double* wbuf = nullptr;
+    size_t wbufcap = 0;
+    double* colnorm = nullptr;  // [npad]
+    int* perm = nullptr;        // [npad]
+    int* iscal = nullptr;       // device ints [16]
+    int* hiscal = nullptr;      // pinned
+    double* meta = nullptr;     // class offsets (int64) + loss normalisers, 256 doubles
+    double* hmeta = nullptr;    // pinned
+    int meta_key = 0;
+    double* tmp = nullptr;      // generic staging buffer
+    size_t tmpcap = 0;
+    int sm_count = 148;
+    // nccl
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    // profiling
+    bool prof = false;
+    double prof_ms[MPST_T_COUNT] = {0};
+    int64_t prof_n[MPST_T_COUNT] = {0};
+    int64_t launches = 0;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+    std::vector<cudaEvent_t> evpool;
+};
+
+#define CUDA_TRY(ctx, expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                      \
+            return MPST_E_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+#define TRY(expr)                                                                                 \
+    do {                                                                                          \
+        int _r = (expr);                                                                          \
+        if (_r != MPST_OK) return _r;                                                             \
+    } while (0)
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---- kernels (defined in the .cu files) -------------------------------------------------------
+int launch_encode(mpst_ctx* c, int basis, int d, const double* x, int64_t n, double* out, int64_t ldo);
+int launch_permute_core(mpst_ctx* c, const double* src, double* dst, int d, int chi_l, int chi_r,
+                        int C, long ss, long sa, long sb, long sc, long ds, long da, long db, long dc);
+int launch_krao_gemm_rows(mpst_ctx* c, const double* x, const double* E, const double* W, double* out,
+                          int64_t row_begin, int64_t row_end, int d, int chi, int n_out, int64_t ldw,
+                          int64_t ldo);
+int launch_krao_gemm(mpst_ctx* c, const double* x, const double* E, const double* W, double* out,
+                     int64_t N, int d, int chi, int n_out, int64_t ldw, int64_t ldo);
+int launch_flatten(mpst_ctx* c, CoreView l, CoreView r, int d, int chi_l, int chi_m, int chi_r, int C,
+                   double* B);
+int launch_sumsq(mpst_ctx* c, const double* v, int64_t n, double* out_dev);
+int launch_axpy(mpst_ctx* c, double* B, const double* G, int64_t n, const double* gnorm2_dev,
+                double eta, int tsgo);
+int launch_scale_dev(mpst_ctx* c, double* v, int64_t n, const double* norm2_dev);
+int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* missing, int64_t n,
+                 int method, const double* xgrid, int G, const double* uniforms, int n_traj,
+                 double max_jump, double* out);
+
+// profiling helpers
+void prof_begin(mpst_ctx* c, int kind);
+void prof_end(mpst_ctx* c, int kind);
+int ensure_buf(mpst_ctx* c, double** p, size_t* cap, size_t need);

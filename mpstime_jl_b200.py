@@ -1,0 +1,12 @@
+"""Import shim: the package lives in the directory `mpstime.jl_b200/` (a dotted name Python cannot
+import directly); this module loads it and re-exports it as `mpstime_jl_b200`."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mpstime.jl_b200")
+_spec = importlib.util.spec_from_file_location(
+    "mpstime_jl_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["mpstime_jl_b200"] = _mod
+_spec.loader.exec_module(_mod)
