@@ -157,9 +157,13 @@ int mpst_bond_split(mpst_ctx* ctx, const double* B, int d, int chi_l, int chi_r,
 /* ---- timing hooks for bench.py: device time (ms, CUDA events on the context's stream) spent in
  *      each kernel family since the last reset, and launch counts. ------------------------ */
 enum { MPST_T_ENCODE = 0, MPST_T_FLATTEN, MPST_T_FWD, MPST_T_GRAD, MPST_T_UPDATE, MPST_T_SVD,
-       MPST_T_ENV, MPST_T_ALLREDUCE, MPST_T_IMPUTE, MPST_T_COUNT };
+       MPST_T_ENV, MPST_T_ALLREDUCE, MPST_T_IMPUTE, MPST_T_GRADK /* bond_grad_kernel alone */, MPST_T_COUNT };
 int mpst_profile_enable(mpst_ctx* ctx, int on);
-int mpst_profile_get(mpst_ctx* ctx, double* ms /*MPST_T_COUNT*/, int64_t* launches /*MPST_T_COUNT*/);
+int mpst_profile_get(mpst_ctx* ctx, double* ms /*MPST_T_COUNT*/, int64_t* launches /*MPST_T_COUNT*/,
+                     double* work /*MPST_T_COUNT: algorithmic flops (GEMM families) or bytes (encode)*/);
+/* device-side stopwatch on the context's stream (CUDA events): start, ..., stop -> elapsed ms */
+int mpst_timer_start(mpst_ctx* ctx);
+int mpst_timer_stop(mpst_ctx* ctx, double* ms);
 int mpst_profile_reset(mpst_ctx* ctx);
 int64_t mpst_launch_count(mpst_ctx* ctx);
 

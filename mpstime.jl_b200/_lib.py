@@ -49,7 +49,9 @@ SIGNATURES = {
     "mpst_bond_split": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_double, c_i32_p, c_double_p, c_double_p, c_double_p]),
     "mpst_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
-    "mpst_profile_get": (C.c_int, [C.c_void_p, c_double_p, c_i64_p]),
+    "mpst_profile_get": (C.c_int, [C.c_void_p, c_double_p, c_i64_p, c_double_p]),
+    "mpst_timer_start": (C.c_int, [C.c_void_p]),
+    "mpst_timer_stop": (C.c_int, [C.c_void_p, c_double_p]),
     "mpst_profile_reset": (C.c_int, [C.c_void_p]),
     "mpst_launch_count": (C.c_int64, [C.c_void_p]),
 }

@@ -15,7 +15,7 @@ BASIS_RANGE = {0: (-1.0, 1.0), 1: (-1.0, 1.0), 2: (-1.0, 1.0), 3: (0.0, 1.0), 4:
 LOSS_IDS = {"KLD": 0, "MSE": 1}
 OPT_IDS = {"TSGO": 0, "GD": 1}
 METHOD_IDS = {"median": 0, "mean": 1, "mode": 2, "ITS": 3}
-TIMER_NAMES = ["encode", "flatten", "fwd", "grad", "update", "svd", "env", "allreduce", "impute"]
+TIMER_NAMES = ["encode", "flatten", "fwd", "grad", "update", "svd", "env", "allreduce", "impute", "grad_kernel"]
 
 
 class MPSTError(RuntimeError):
@@ -258,10 +258,20 @@ class Context:
         self._chk(self.lib.mpst_profile_reset(self.h))
 
     def profile_get(self):
+        """{family: (device ms, launches, algorithmic work)} since the last reset."""
         ms = np.zeros(len(TIMER_NAMES))
         n = np.zeros(len(TIMER_NAMES), dtype=np.int64)
-        self._chk(self.lib.mpst_profile_get(self.h, _dp(ms), n.ctypes.data_as(c_i64_p)))
-        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(TIMER_NAMES)}
+        wk = np.zeros(len(TIMER_NAMES))
+        self._chk(self.lib.mpst_profile_get(self.h, _dp(ms), n.ctypes.data_as(c_i64_p), _dp(wk)))
+        return {k: (float(ms[i]), int(n[i]), float(wk[i])) for i, k in enumerate(TIMER_NAMES)}
+
+    def timer_start(self):
+        self._chk(self.lib.mpst_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._chk(self.lib.mpst_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def launch_count(self):
         return int(self.lib.mpst_launch_count(self.h))

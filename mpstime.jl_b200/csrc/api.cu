@@ -478,6 +478,12 @@ static int loss_grad_device(mpst_ctx* c, const double* phl, const double* phr, c
     {
         ProfScope ps(c, MPST_T_GRAD);
         std::vector<int64_t> cb(C), ce(C);
+        {
+            const double ns = loss_kind == MPST_LOSS_KLD ? (double)c->N : (double)c->N * C;
+            c->prof_work[MPST_T_GRAD] += 2.0 * ns * (double)D;
+            c->prof_work[MPST_T_GRADK] += 2.0 * ns * (double)D;
+            c->prof_work[MPST_T_FWD] += 2.0 * ns * (double)D;
+        }
         for (int cls = 0; cls < C; cls++) {
             cb[cls] = loss_kind == MPST_LOSS_KLD ? c->class_off[cls] : 0;
             ce[cls] = loss_kind == MPST_LOSS_KLD ? c->class_off[cls + 1] : c->N;
@@ -593,12 +599,14 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         kr.chi_l = chi_new; kr.has_label = 0; kr.orient = ORIENT_RIGHT;
         ProfScope ps(c, MPST_T_ENV);     // update_caches! :124-131
         TRY(launch_krao_gemm(c, phr, R, kr.dev, slot_ptr(c, r), c->N, d, chi_r, chi_new, Dr, chi_new));
+        c->prof_work[MPST_T_ENV] += 2.0 * (double)c->N * Dr * chi_new;
         c->env_chi[r] = chi_new;
     } else {                // W[l] <- U (LEFT), W[r] <- V*S with the label (RIGHT)   (:177-196)
         kl.chi_r = chi_new; kl.has_label = 0; kl.orient = ORIENT_LEFT;
         kr.chi_l = chi_new; kr.has_label = 1; kr.orient = ORIENT_RIGHT;
         ProfScope ps(c, MPST_T_ENV);     // update_caches! :132-141
         TRY(launch_krao_gemm(c, phl, L, kl.dev, slot_ptr(c, l), c->N, d, chi_l, chi_new, Dl, chi_new));
+        c->prof_work[MPST_T_ENV] += 2.0 * (double)c->N * Dl * chi_new;
         c->env_chi[l] = chi_new;
     }
     if (chi_new_out) *chi_new_out = chi_new;
@@ -848,14 +856,35 @@ int mpst_profile_enable(mpst_ctx* c, int on) { if (!c) return MPST_E_INVALID; c-
 int mpst_profile_reset(mpst_ctx* c) {
     if (!c) return MPST_E_INVALID;
     prof_drain(c);
-    for (int k = 0; k < MPST_T_COUNT; k++) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
+    for (int k = 0; k < MPST_T_COUNT; k++) { c->prof_ms[k] = 0; c->prof_n[k] = 0; c->prof_work[k] = 0; }
     c->launches = 0;
     return MPST_OK;
 }
-int mpst_profile_get(mpst_ctx* c, double* ms, int64_t* launches) {
+int mpst_profile_get(mpst_ctx* c, double* ms, int64_t* launches, double* work) {
     if (!c) return MPST_E_INVALID;
     prof_drain(c);
-    for (int k = 0; k < MPST_T_COUNT; k++) { if (ms) ms[k] = c->prof_ms[k]; if (launches) launches[k] = c->prof_n[k]; }
+    for (int k = 0; k < MPST_T_COUNT; k++) {
+        if (ms) ms[k] = c->prof_ms[k];
+        if (launches) launches[k] = c->prof_n[k];
+        if (work) work[k] = c->prof_work[k];
+    }
+    return MPST_OK;
+}
+int mpst_timer_start(mpst_ctx* c) {
+    if (!c) return MPST_E_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->tm0) { CUDA_TRY(c, cudaEventCreate(&c->tm0)); CUDA_TRY(c, cudaEventCreate(&c->tm1)); }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaEventRecord(c->tm0, c->stream));
+    return MPST_OK;
+}
+int mpst_timer_stop(mpst_ctx* c, double* ms) {
+    if (!c || !ms || !c->tm0) return MPST_E_INVALID;
+    CUDA_TRY(c, cudaEventRecord(c->tm1, c->stream));
+    CUDA_TRY(c, cudaEventSynchronize(c->tm1));
+    float f = 0.f;
+    CUDA_TRY(c, cudaEventElapsedTime(&f, c->tm0, c->tm1));
+    *ms = f;
     return MPST_OK;
 }
 int64_t mpst_launch_count(mpst_ctx* c) { return c ? c->launches : 0; }

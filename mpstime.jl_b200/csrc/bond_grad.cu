@@ -256,8 +256,10 @@ int launch_bond_grad(mpst_ctx* c, const double* xl, const double* xr, const doub
 
     const size_t smem = 16 + sizeof(double) * (2 * (size_t)KC * (chi_l + chi_r + 2 * d + 1) + 4 * (size_t)KC * LDT);
     CUDA_TRY(c, cudaFuncSetAttribute(bond_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(c, MPST_T_GRADK);
     bond_grad_kernel<<<ncta, 256, smem, c->stream>>>(xl, xr, L, R, c->w, c->Npad, d, chi_l, chi_r, c->segs,
                                                     c->cta_ptr, c->part);
+    prof_end(c, MPST_T_GRADK);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
     grad_reduce_kernel<<<ntiles, 256, 0, c->stream>>>(c->part, c->tile_slot, ntp, ntq, Dl, Dr, G);

@@ -101,6 +101,8 @@ struct mpst_ctx {
     bool prof = false;
     double prof_ms[MPST_T_COUNT] = {0};
     int64_t prof_n[MPST_T_COUNT] = {0};
+    double prof_work[MPST_T_COUNT] = {0};
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;
     int64_t launches = 0;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
     std::vector<cudaEvent_t> evpool;

@@ -14,10 +14,11 @@
 // (fixed pairing and summation order), so replicated ranks stay bit-identical.
 // Truncation: NDTensors rule on P = sigma^2 (maxdim, then relative cutoff on the *sum* of
 // discarded weight), evaluated on the device.
+#include <cstdio>
+#include <cstdlib>
 #include "mpst_common.cuh"
 
 namespace {
-constexpr int JB = 16, PB = 2 * JB;      // block width, pair width
 constexpr int GR = 64;                   // rows per Gram chunk
 
 __device__ __forceinline__ void rr_pair(int nb, int st, int k, int& I, int& J) {
@@ -53,9 +54,12 @@ jac_load_kernel(const double* __restrict__ B, double* __restrict__ S, int going_
     S[(size_t)col * ld + r] = v;
 }
 
+// Gram matrix of one column-block pair over a row slice.  256 threads, each a (PB/16)x(PB/16) block.
+template <int PB>
 __global__ void __launch_bounds__(256)
 jac_gram_kernel(const double* __restrict__ S, int64_t ld, int m, int nb, int st, int rsplit,
                 double* __restrict__ gpart) {
+    constexpr int JB = PB / 2, R = PB / 16;
     __shared__ double T[PB][GR + 1];
     int I, J;
     rr_pair(nb, st, blockIdx.x, I, J);
@@ -64,57 +68,73 @@ jac_gram_kernel(const double* __restrict__ S, int64_t ld, int m, int nb, int st,
     const int c0 = (int)(((int64_t)nchunks * split) / rsplit), c1 = (int)(((int64_t)nchunks * (split + 1)) / rsplit);
     const int tid = threadIdx.x;
     const int u = tid & 15, v = tid >> 4;
-    double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
-    const int lr = tid & 63, lg = tid >> 6;                 // loader: row, column group of 8
+    double acc[R][R];
+#pragma unroll
+    for (int i = 0; i < R; i++)
+#pragma unroll
+        for (int j = 0; j < R; j++) acc[i][j] = 0.0;
+    const int lr = tid & 63, lg = tid >> 6;                 // loader: row, column group
     for (int ch = c0; ch < c1; ch++) {
         const int r = ch * GR + lr;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int cc = lg * 8 + k;
+        for (int k = 0; k < PB / 4; k++) {
+            const int cc = lg * (PB / 4) + k;
             const int col = (cc < JB) ? I * JB + cc : J * JB + (cc - JB);
             T[cc][lr] = (r < m) ? S[(size_t)col * ld + r] : 0.0;
         }
         __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
         for (int rr = 0; rr < GR; rr++) {
-            const double x0 = T[2 * u][rr], x1 = T[2 * u + 1][rr];
-            const double y0 = T[2 * v][rr], y1 = T[2 * v + 1][rr];
-            a00 += x0 * y0; a01 += x0 * y1; a10 += x1 * y0; a11 += x1 * y1;
+            double x[R], y[R];
+#pragma unroll
+            for (int i = 0; i < R; i++) { x[i] = T[R * u + i][rr]; y[i] = T[R * v + i][rr]; }
+#pragma unroll
+            for (int i = 0; i < R; i++)
+#pragma unroll
+                for (int j = 0; j < R; j++) acc[i][j] += x[i] * y[j];
         }
         __syncthreads();
     }
     double* g = gpart + ((size_t)blockIdx.x * rsplit + split) * PB * PB;
-    g[(2 * u) * PB + 2 * v] = a00;
-    g[(2 * u) * PB + 2 * v + 1] = a01;
-    g[(2 * u + 1) * PB + 2 * v] = a10;
-    g[(2 * u + 1) * PB + 2 * v + 1] = a11;
+#pragma unroll
+    for (int i = 0; i < R; i++)
+#pragma unroll
+        for (int j = 0; j < R; j++) g[(R * u + i) * PB + R * v + j] = acc[i][j];
 }
 
-// eigen-decomposition of the pair Gram matrix; W[v][u] = component v of eigenvector u
-__global__ void __launch_bounds__(256)
+// Rotation matrix of the pair: `inner_sweeps` cyclic two-sided Jacobi sweeps on the PBxPB Gram matrix in
+// shared memory (PB/2 disjoint rotations per round, 16 threads per rotation).  A pair (p,q) is rotated only
+// if |a_pq| > tol*sqrt(a_pp a_qq) AND |a_pq| > floor_abs: entries below the absolute floor (a fraction of
+// eps*||M||_F^2, far below the truncation cutoff) are rounding-level couplings between numerically null
+// directions -- LAPACK's gesdd does not resolve them either -- and chasing them stalls convergence.
+// W[v][u] = component v of new column u.
+template <int PB>
+__global__ void __launch_bounds__(PB * 8)
 jac_solve_kernel(const double* __restrict__ gpart, int rsplit, double* __restrict__ wbuf, double tol,
-                 double negl, unsigned long long* __restrict__ maxoff_bits) {
-    __shared__ double A[PB][PB + 1];
-    __shared__ double V[PB][PB + 1];
-    __shared__ double cs[JB][2];
+                 double abs_tol, const double* __restrict__ trace_dev, int inner_sweeps,
+                 unsigned long long* __restrict__ maxoff_bits) {
+    constexpr int NT = PB * 8;
+    extern __shared__ double jsm[];
+    double (*A)[PB + 1] = reinterpret_cast<double (*)[PB + 1]>(jsm);
+    double (*V)[PB + 1] = reinterpret_cast<double (*)[PB + 1]>(jsm + PB * (PB + 1));
     __shared__ int any_rot;
     const int tid = threadIdx.x;
+    const double floor_abs = abs_tol * (trace_dev ? *trace_dev : 1.0);
     const double* g = gpart + (size_t)blockIdx.x * rsplit * PB * PB;
-    for (int e = tid; e < PB * PB; e += 256) {
+    for (int e = tid; e < PB * PB; e += NT) {
         double s = 0.0;
         for (int k = 0; k < rsplit; k++) s += g[(size_t)k * PB * PB + e];
         A[e / PB][e % PB] = s;
         V[e / PB][e % PB] = (e / PB == e % PB) ? 1.0 : 0.0;
     }
     __syncthreads();
-    // symmetrise (partials are computed as full blocks; keep exact symmetry) + convergence measure
-    double mo = 0.0;
-    for (int e = tid; e < PB * PB; e += 256) {
+    double mo = 0.0;                                        // convergence measure before rotating
+    for (int e = tid; e < PB * PB; e += NT) {
         const int r = e / PB, cidx = e % PB;
         if (r < cidx) {
-            const double apq = 0.5 * (A[r][cidx] + A[cidx][r]);
+            const double apq = fabs(A[r][cidx]);
             const double den = A[r][r] * A[cidx][cidx];
-            if (den > negl * negl && apq != 0.0) mo = fmax(mo, fabs(apq) / sqrt(den));
+            if (apq > floor_abs && den > 0.0) mo = fmax(mo, apq * rsqrt(den));
         }
     }
 #pragma unroll
@@ -123,7 +143,7 @@ jac_solve_kernel(const double* __restrict__ gpart, int rsplit, double* __restric
     __syncthreads();
 
     const int k = tid >> 4, l16 = tid & 15;
-    for (int sweep = 0; sweep < 40; sweep++) {
+    for (int sweep = 0; sweep < inner_sweeps; sweep++) {
         if (tid == 0) any_rot = 0;
         __syncthreads();
         for (int rd = 0; rd < PB - 1; rd++) {
@@ -131,16 +151,18 @@ jac_solve_kernel(const double* __restrict__ gpart, int rsplit, double* __restric
             rr_pair(PB, rd, k, p, q);
             const double app = A[p][p], aqq = A[q][q], apq = A[p][q];
             double c = 1.0, s = 0.0;
-            if (apq != 0.0 && fabs(apq) > tol * sqrt(fabs(app * aqq))) {
-                const double tau = (aqq - app) / (2.0 * apq);
-                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                c = 1.0 / sqrt(1.0 + t * t);
+            const double aa = fabs(apq);
+            if (aa > floor_abs && aa > tol * sqrt(fabs(app * aqq))) {
+                // t = sgn(tau)/(|tau| + sqrt(1+tau^2)), tau = (aqq-app)/(2 apq), written division-light
+                const double zeta = aqq - app, beta = 2.0 * apq;
+                const double t = (zeta >= 0.0 ? beta : -beta) / (fabs(zeta) + sqrt(zeta * zeta + beta * beta));
+                c = rsqrt(1.0 + t * t);
                 s = t * c;
                 if (l16 == 0) any_rot = 1;
             }
             __syncthreads();
 #pragma unroll
-            for (int h = 0; h < 2; h++) {               // columns p, q of A and V
+            for (int h = 0; h < PB / 16; h++) {             // columns p, q of A and V
                 const int r = l16 + 16 * h;
                 const double x = A[r][p], y = A[r][q];
                 A[r][p] = c * x - s * y;
@@ -151,7 +173,7 @@ jac_solve_kernel(const double* __restrict__ gpart, int rsplit, double* __restric
             }
             __syncthreads();
 #pragma unroll
-            for (int h = 0; h < 2; h++) {               // rows p, q of A
+            for (int h = 0; h < PB / 16; h++) {             // rows p, q of A
                 const int cc = l16 + 16 * h;
                 const double x = A[p][cc], y = A[q][cc];
                 A[p][cc] = c * x - s * y;
@@ -163,18 +185,20 @@ jac_solve_kernel(const double* __restrict__ gpart, int rsplit, double* __restric
         __syncthreads();
     }
     double* w = wbuf + (size_t)blockIdx.x * PB * PB;
-    for (int e = tid; e < PB * PB; e += 256) w[e] = V[e / PB][e % PB];
+    for (int e = tid; e < PB * PB; e += NT) w[e] = V[e / PB][e % PB];
 }
 
-__global__ void __launch_bounds__(256)
+template <int PB>
+__global__ void __launch_bounds__(128)
 jac_apply_kernel(double* __restrict__ S, int64_t ld, int mm, int nb, int st, const double* __restrict__ wbuf) {
+    constexpr int JB = PB / 2;
     __shared__ double W[PB][PB];
     int I, J;
     rr_pair(nb, st, blockIdx.x, I, J);
     const double* w = wbuf + (size_t)blockIdx.x * PB * PB;
-    for (int e = threadIdx.x; e < PB * PB; e += 256) W[e / PB][e % PB] = w[e];
+    for (int e = threadIdx.x; e < PB * PB; e += 128) W[e / PB][e % PB] = w[e];
     __syncthreads();
-    const int r = blockIdx.y * 256 + threadIdx.x;
+    const int r = blockIdx.y * 128 + threadIdx.x;
     if (r >= mm) return;
     double x[PB];
 #pragma unroll
@@ -182,13 +206,13 @@ jac_apply_kernel(double* __restrict__ S, int64_t ld, int mm, int nb, int st, con
         const int col = (v < JB) ? I * JB + v : J * JB + (v - JB);
         x[v] = S[(size_t)col * ld + r];
     }
-#pragma unroll 4
+#pragma unroll 2
     for (int u = 0; u < PB; u++) {
-        double s = 0.0;
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int v = 0; v < PB; v++) s += x[v] * W[v][u];
+        for (int v = 0; v < PB; v += 2) { s0 += x[v] * W[v][u]; s1 += x[v + 1] * W[v + 1][u]; }
         const int col = (u < JB) ? I * JB + u : J * JB + (u - JB);
-        S[(size_t)col * ld + r] = s;
+        S[(size_t)col * ld + r] = s0 + s1;
     }
 }
 
@@ -261,6 +285,56 @@ jac_gather_kernel(const double* __restrict__ S, int64_t ld, int m, int n, int C,
 }
 }  // namespace
 
+template <int PB>
+static int jacobi_sweeps(mpst_ctx* c, int m, int n, int npad, int64_t ld, double cutoff, const double* trace_dev,
+                         int* sweeps_out) {
+    constexpr int JB = PB / 2;
+    const int nb = npad / JB;                    // even
+    const int npairs = nb / 2;
+    const int mm = m + n;
+    int rsplit = std::max(1, std::min((m + GR - 1) / GR, (2 * c->sm_count + npairs - 1) / npairs));
+    TRY(ensure_buf(c, &c->gpart, &c->gpartcap, (size_t)npairs * rsplit * PB * PB));
+    TRY(ensure_buf(c, &c->wbuf, &c->wbufcap, (size_t)npairs * PB * PB));
+    unsigned long long* maxoff = reinterpret_cast<unsigned long long*>(c->scal + 8);
+    const double eps = 2.220446049250313e-16;
+    const double tol = 1e-15;
+    // The measure is taken BEFORE a sweep's rotations.  Jacobi converges quadratically, so a sweep that starts
+    // with every relative off-diagonal <= 1e-8 ends with them <= ~1e-16: stop after it, no verification sweep.
+    const double conv = 1e-8;
+    const double abs_tol = std::max(1e-30, std::min(0.5 * eps, 1e-6 * cutoff));
+    const int inner = getenv("MPST_SVD_INNER") ? atoi(getenv("MPST_SVD_INNER")) : 1;
+    const size_t solve_smem = 2 * sizeof(double) * PB * (PB + 1);
+    CUDA_TRY(c, cudaFuncSetAttribute(jac_solve_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+    int sweeps = 0;
+    const int max_sweeps = 60;
+    bool converged = false;
+    std::string hist;
+    for (; sweeps < max_sweeps && !converged; sweeps++) {
+        CUDA_TRY(c, cudaMemsetAsync(maxoff, 0, sizeof(unsigned long long), c->stream));
+        for (int st = 0; st < nb - 1; st++) {
+            jac_gram_kernel<PB><<<dim3(npairs, rsplit), 256, 0, c->stream>>>(c->S, ld, m, nb, st, rsplit, c->gpart);
+            jac_solve_kernel<PB><<<npairs, PB * 8, solve_smem, c->stream>>>(c->gpart, rsplit, c->wbuf, tol, abs_tol, trace_dev, inner, maxoff);
+            jac_apply_kernel<PB><<<dim3(npairs, (mm + 127) / 128), 128, 0, c->stream>>>(c->S, ld, mm, nb, st, c->wbuf);
+            c->launches += 3;
+        }
+        CUDA_TRY(c, cudaGetLastError());
+        CUDA_TRY(c, cudaMemcpyAsync(c->hscal + 8, maxoff, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        if (c->hscal[8] <= conv) converged = true;
+        if (sweeps < 64) { char b[32]; snprintf(b, sizeof b, " %.2e", c->hscal[8]); hist += b; }
+        if (!(c->hscal[8] == c->hscal[8])) break;                 // NaN in the bond tensor
+    }
+    if (getenv("MPST_SVD_DEBUG")) fprintf(stderr, "[svd] m=%d n=%d PB=%d sweeps=%d:%s\n", m, n, PB, sweeps, hist.c_str());
+    if (!converged) {
+        char b[160];
+        snprintf(b, sizeof b, "svd: Jacobi did not converge (m=%d n=%d conv=%.2e) max-offdiag per sweep:", m, n, conv);
+        c->err = std::string(b) + hist;
+        return MPST_E_NUMERIC;
+    }
+    if (sweeps_out) *sweeps_out = sweeps;
+    return MPST_OK;
+}
+
 // B: [C][Dl*Dr] on the device.  Writes the two new cores into label_core / ortho_core (device,
 // capacity checked by the caller) and returns chi_new (host) after one small D2H copy.
 // norm2_dev != nullptr: B is scaled by 1/sqrt(*norm2_dev) on load (fused renormalisation).
@@ -269,15 +343,12 @@ int svd_split_device(mpst_ctx* c, const double* B, int Dl, int Dr, int C, int go
                      int* chi_new, double* sigma_host, int* sweeps_out) {
     const int n = going_left ? Dr : Dl;
     const int m = C * (going_left ? Dl : Dr);
-    const int npad = (int)round_up(n, PB);
-    const int nb = npad / JB;                    // even
-    const int npairs = nb / 2;
+    const bool wide = getenv("MPST_SVD_PB64") != nullptr && n >= 256;
+    const int PBsel = wide ? 64 : 32;
+    const int npad = (int)round_up(n, PBsel);
     const int mm = m + n;
     const int64_t ld = round_up(mm, 2);
     TRY(ensure_buf(c, &c->S, &c->Scap, (size_t)ld * npad));
-    int rsplit = std::max(1, std::min((m + GR - 1) / GR, (2 * c->sm_count + npairs - 1) / npairs));
-    TRY(ensure_buf(c, &c->gpart, &c->gpartcap, (size_t)npairs * rsplit * PB * PB));
-    TRY(ensure_buf(c, &c->wbuf, &c->wbufcap, (size_t)npairs * PB * PB));
     {
         const int64_t tot = (int64_t)mm * npad;
         jac_load_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(B, c->S, going_left, Dl, Dr, C, m, n, npad,
@@ -285,27 +356,14 @@ int svd_split_device(mpst_ctx* c, const double* B, int Dl, int Dr, int C, int go
         c->launches++;
         CUDA_TRY(c, cudaGetLastError());
     }
-    unsigned long long* maxoff = reinterpret_cast<unsigned long long*>(c->scal + 8);
-    const double tol = 1e-15, negl = 1e-26;
-    const double conv = 8.0 * 2.220446049250313e-16 * sqrt((double)m);   // LAPACK dgesvj-style sqrt(m)*eps
-    int sweeps = 0;
-    const int max_sweeps = 40;
-    bool converged = false;
-    for (; sweeps < max_sweeps && !converged; sweeps++) {
-        CUDA_TRY(c, cudaMemsetAsync(maxoff, 0, sizeof(unsigned long long), c->stream));
-        for (int st = 0; st < nb - 1; st++) {
-            jac_gram_kernel<<<dim3(npairs, rsplit), 256, 0, c->stream>>>(c->S, ld, m, nb, st, rsplit, c->gpart);
-            jac_solve_kernel<<<npairs, 256, 0, c->stream>>>(c->gpart, rsplit, c->wbuf, tol, negl, maxoff);
-            jac_apply_kernel<<<dim3(npairs, (mm + 255) / 256), 256, 0, c->stream>>>(c->S, ld, mm, nb, st, c->wbuf);
-            c->launches += 3;
-        }
-        CUDA_TRY(c, cudaGetLastError());
-        CUDA_TRY(c, cudaMemcpyAsync(c->hscal + 8, maxoff, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        if (c->hscal[8] <= conv) converged = true;
+    // ||M||_F^2 for the absolute rotation floor: 1 when the load normalises, else computed here
+    const double* trace_dev = nullptr;
+    if (!norm2_dev) {
+        TRY(launch_sumsq(c, B, (int64_t)Dl * Dr * C, c->scal + 5));
+        trace_dev = c->scal + 5;
     }
-    if (!converged) { c->err = "svd: Jacobi did not converge"; return MPST_E_NUMERIC; }
-    if (sweeps_out) *sweeps_out = sweeps;
+    if (wide) TRY(jacobi_sweeps<64>(c, m, n, npad, ld, cutoff, trace_dev, sweeps_out));
+    else TRY(jacobi_sweeps<32>(c, m, n, npad, ld, cutoff, trace_dev, sweeps_out));
     jac_colnorm_kernel<<<npad, 128, 0, c->stream>>>(c->S, ld, m, c->colnorm);
     jac_sort_trunc_kernel<<<1, 1024, 0, c->stream>>>(c->colnorm, n, npad, chi_max, cutoff, c->perm, c->colnorm + npad, c->iscal);
     jac_gather_kernel<<<2 * c->sm_count, 256, 0, c->stream>>>(c->S, ld, m, n, C, c->perm, c->iscal, label_core, ortho_core);

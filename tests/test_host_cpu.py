@@ -1,0 +1,150 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the host
+preprocessing mirrors the oracle, option validation mirrors the reference's errors, and the
+sample-sharding plan reproduces the full gradient (world_size 2, gloo)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    header = open(os.path.join(ROOT, "include", "mpstime_b200.h")).read()
+    declared = set(re.findall(r"\b(mpst_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mpst_ctx", "mpst_train_opts"}
+    assert len(declared) >= 20
+    assert declared == set(pkg.SIGNATURES), declared ^ set(pkg.SIGNATURES)
+    from mpstime_jl_b200 import _lib
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.mpst_version() >= 100
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.MPSTError):
+        pkg.Context(0)
+
+
+def test_product_never_imports_oracle():
+    pkgdir = os.path.join(ROOT, "mpstime.jl_b200")
+    for dirpath, _, files in os.walk(pkgdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "mpstime_oracle" not in src and "oracle/" not in src, f
+
+
+def test_preprocess_matches_oracle(pkg, oracle):
+    rng = np.random.default_rng(0)
+    Xtr = rng.standard_normal((50, 20)).cumsum(axis=1)
+    Xte = 1.3 * rng.standard_normal((9, 20)).cumsum(axis=1)
+    opts = pkg.MPSOptions()
+    Xs, norms = pkg.transform_train_data(Xtr.T, opts)
+    Xo, no = oracle.transform_train_data(Xtr.T)
+    assert np.array_equal(Xs, Xo)
+    Xt, oob = pkg.transform_test_data(Xte.T, norms, opts)
+    Xto, oobo = oracle.transform_test_data(Xte.T, no)
+    assert np.array_equal(Xt, Xto) and oob == oobo
+    back = pkg.invert_test_transform(Xt, oob, norms, opts)
+    backo = oracle.invert_test_transform(Xto, oobo, no)
+    assert np.array_equal(np.isnan(back), np.isnan(backo)) and np.allclose(back, backo, equal_nan=True)
+    opts2 = pkg.MPSOptions(sigmoid_transform=False, data_bounds=(0.1, 0.9))
+    Xs2, n2 = pkg.transform_train_data(Xtr.T, opts2)
+    Xo2, _ = oracle.transform_train_data(Xtr.T, sigmoid_transform=False, data_bounds=(0.1, 0.9))
+    assert np.array_equal(Xs2, Xo2) and abs(Xs2.min() + 0.8) < 1e-12 and abs(Xs2.max() - 0.8) < 1e-12
+    # golden: the reference's own saved data (see test_oracle.py)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ecg200_legendre.npz"))
+    Xg, _ = pkg.transform_train_data(g["X_orig"].T, opts)
+    assert np.abs(np.sqrt(1.5) * Xg.T - g["phi_ref"][:, :, 1]).max() < 1e-14
+
+
+def test_sort_and_start_mps(pkg, oracle):
+    y = np.array([1, 0, 1, 0, 2, 0])
+    X = np.arange(12.0).reshape(2, 6)
+    Xs, _, ys, order, classes, counts = pkg.sort_by_class(X, None, y)
+    assert list(order) == [1, 3, 5, 0, 2, 4] and list(counts) == [3, 2, 1] and list(classes) == [0, 1, 2]
+    cores = pkg.generate_starting_mps(4, 7, 3, 2, seed=1)
+    assert cores[-1].shape == (3, 3, 1, 2) and cores[0].shape == (1, 3, 3)
+    assert abs(oracle._norm2_general(cores) - 1.0) < 1e-12
+    for A in cores[:-1]:                                   # left-orthonormal
+        a, s, b = A.shape
+        M = A.reshape(a * s, b)
+        assert np.abs(M.T @ M - np.eye(b)).max() < 1e-12
+
+
+def test_option_validation_mirrors_reference(pkg):
+    with pytest.raises(ValueError, match="Optim"):
+        pkg.MPSOptions(bbopt="Optim")._check()
+    with pytest.raises(ValueError):
+        pkg.MPSOptions(encoding="Fourier")._check()
+    assert pkg.MPSOptions()._check() == "legendre_no_norm"
+    o = pkg.MPSOptions()
+    assert (o.nsweeps, o.chi_max, o.eta, o.d, o.cutoff, o.chi_init, o.init_rng) == (10, 25, 0.01, 5, 1e-10, 4, 1234)
+    clf = pkg.MPSClassifier()
+    assert (clf.nsweeps, clf.chi_max, clf.d, clf.exit_early) == (5, 15, 2, True)
+
+
+def test_shard_ranges(pkg):
+    counts = [7, 5, 11]
+    for world in (1, 2, 3, 8):
+        seen = []
+        for r in range(world):
+            rg = pkg.dist.shard_ranges(counts, r, world)
+            assert len(rg) == 3
+            seen.append(rg)
+        for c in range(3):
+            off = sum(counts[:c])
+            assert seen[0][c][0] == off and seen[-1][c][1] == off + counts[c]
+            for r in range(world - 1):
+                assert seen[r][c][1] == seen[r + 1][c][0]
+
+
+_GLOO_SCRIPT = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "oracle"))
+import numpy as np, torch, torch.distributed as td
+import mpstime_oracle as o
+import mpstime_jl_b200 as m
+td.init_process_group("gloo")
+rank, world = td.get_rank(), td.get_world_size()
+assert m.dist.rank_world() == (rank, world)
+rng = np.random.default_rng(0)
+N, d, cl, cr, C = 41, 3, 4, 5, 2
+counts = np.array([17, 24])
+xl = o.legendre_encode(rng.uniform(-1, 1, N), d); xr = o.legendre_encode(rng.uniform(-1, 1, N), d)
+L = rng.standard_normal((N, cl)); R = rng.standard_normal((N, cr))
+B = rng.standard_normal((d * cl * d * cr, C))
+for loss in ("KLD", "MSE"):
+    fn = o.loss_grad_KLD if loss == "KLD" else o.loss_grad_MSE
+    lo_full, G_full = fn(B, L, R, xl, xr, counts)
+    X = np.arange(N, dtype=np.float64)[None, :]
+    _, cloc, idx = m.dist.shard_samples(X, counts, rank, world)
+    lo_loc, G_loc = fn(B, L[idx], R[idx], xl[idx], xr[idx], cloc)
+    # local normaliser is the LOCAL N; the device kernel uses the global one: rescale, then sum
+    buf = torch.from_numpy(np.concatenate([G_loc.reshape(-1) * len(idx) / N, [lo_loc * len(idx) / N]]))
+    td.all_reduce(buf)
+    G = buf[:-1].numpy().reshape(G_full.shape); lo = float(buf[-1])
+    assert abs(lo - lo_full) < 1e-12 * abs(lo_full), (lo, lo_full)
+    assert np.abs(G - G_full).max() < 1e-12 * np.abs(G_full).max()
+td.barrier()
+if rank == 0: print("GLOO_OK")
+'''
+
+
+def test_sharded_gradient_allreduce_gloo(tmp_path):
+    """N>1 host logic on CPU: per-class sharding + one all-reduce of [grad, loss] == full result."""
+    script = tmp_path / "gloo_case.py"
+    script.write_text(_GLOO_SCRIPT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29731", str(script), ROOT],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert "GLOO_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -1,0 +1,155 @@
+"""CPU tests of the oracle itself: pinned against the reference's own serialized output where that
+exists (tests/golden/ecg200_legendre.npz, made by tests/golden/make_golden_from_jld2.py), otherwise
+self-consistency (literal loop form == vectorised form, gradient == finite differences, ...)."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ecg200_legendre.npz")
+
+
+def test_golden_normalisation_and_legendre(oracle):
+    """The reference's saved PStates (ECG200, Legendre_No_Norm d=5, sigmoid+minmax) are reproduced from
+    its saved raw matrix: pins transform_train_data (utils.jl:161-200) and legendre_encode
+    (bases.jl:77-92) to 1e-14."""
+    g = np.load(GOLD)
+    Xs, norms = oracle.transform_train_data(g["X_orig"].T)
+    assert Xs.min() == -1.0 and Xs.max() == 1.0
+    phi = oracle.encode(Xs.T, 5, "legendre_no_norm")
+    assert np.abs(phi - g["phi_ref"]).max() < 1e-14
+
+
+def test_legendre_orthonormal(oracle):
+    x, w = np.polynomial.legendre.leggauss(64)
+    phi = oracle.legendre_encode(x, 16)
+    gram = (phi * w[:, None]).T @ phi
+    assert np.abs(gram - np.eye(16)).max() < 1e-12
+    assert np.allclose(oracle.legendre_encode(x, 6, norm=True), oracle.legendre_encode(x, 6) / np.sqrt(np.sqrt(6.5) * 6))
+
+
+def test_fourier_sahand_stoudenmire(oracle):
+    assert list(oracle.fourier_freqs(6)) == [0, 1, -1, 2, -2, 3]
+    x = np.linspace(0, 1, 11)
+    f = oracle.fourier_encode(2 * x - 1, 5)
+    assert np.allclose(np.sum(np.abs(f) ** 2, axis=-1), 1.0)
+    s = oracle.stoudenmire_encode(x)
+    assert np.allclose(np.sum(np.abs(s) ** 2, axis=-1), 1.0)
+    sa = oracle.sahand_encode(x, 4)
+    assert sa.shape == (11, 4) and np.all(np.abs(sa[0, 2:]) == 0)
+
+
+def test_transform_roundtrip_and_oob(oracle):
+    rng = np.random.default_rng(0)
+    Xtr = rng.standard_normal((30, 40))
+    Xs, norms = oracle.transform_train_data(Xtr)
+    assert Xs.min() >= -1 and Xs.max() <= 1
+    Xte = 1.5 * rng.standard_normal((30, 7))
+    Xt, oob = oracle.transform_test_data(Xte, norms)
+    assert Xt.min() >= -1 - 1e-12 and Xt.max() <= 1 + 1e-12 and len(oob) > 0
+    back = oracle.invert_test_transform(Xt, oob, norms)
+    ok = np.isfinite(back)
+    assert ok.mean() > 0.9 and np.abs(back[ok] - Xte[ok]).max() < 1e-8
+
+
+def _problem(oracle, N=40, T=8, d=4, C=2, seed=1):
+    X, y = oracle.synthetic_two_class(N, T, seed=seed)
+    Xs, _ = oracle.transform_train_data(X.T)
+    phi, ys, order, counts, classes = oracle.encode_dataset(Xs, y, d)
+    cores = oracle.random_start_mps(T, d, 4, C, seed=3)
+    return phi, ys, counts, cores
+
+
+def test_loss_grad_loop_vs_vectorised_and_fd(oracle):
+    phi, ys, counts, cores = _problem(oracle)
+    N, T, d = phi.shape
+    LE = oracle.construct_caches(cores, phi, True)
+    l, r = T - 2, T - 1
+    B, dims = oracle.flatten_bt(cores[l], cores[r])
+    L, R = LE[l - 1], np.ones((N, 1))
+    xl, xr = phi[:, l], phi[:, r]
+    for sep in (False, True):
+        a = oracle.loss_grad_KLD_loop(B, L, R, xl, xr, counts, sep)
+        b = oracle.loss_grad_KLD(B, L, R, xl, xr, counts, sep)
+        assert abs(a[0] - b[0]) < 1e-12 and np.abs(a[1] - b[1]).max() < 1e-10
+    a = oracle.loss_grad_MSE_loop(B, L, R, xl, xr, counts)
+    b = oracle.loss_grad_MSE(B, L, R, xl, xr, counts)
+    assert abs(a[0] - b[0]) < 1e-13 and np.abs(a[1] - b[1]).max() < 1e-13
+    rng = np.random.default_rng(0)
+    E = rng.standard_normal(B.shape)
+    eps = 1e-6
+    lo, G = oracle.loss_grad_KLD(B, L, R, xl, xr, counts)
+    fd = (oracle.loss_grad_KLD(B + eps * E, L, R, xl, xr, counts)[0] - oracle.loss_grad_KLD(B - eps * E, L, R, xl, xr, counts)[0]) / (2 * eps)
+    assert abs(fd - 2 * np.sum(G * E)) < 1e-5 * abs(fd)      # the reference's KLD gradient omits the factor 2
+    lo, G = oracle.loss_grad_MSE(B, L, R, xl, xr, counts)
+    fd = (oracle.loss_grad_MSE(B + eps * E, L, R, xl, xr, counts)[0] - oracle.loss_grad_MSE(B - eps * E, L, R, xl, xr, counts)[0]) / (2 * eps)
+    assert abs(fd - np.sum(G * E)) < 1e-6 * max(1.0, abs(fd))
+    # bond overlap == full chain contraction, KLD loss == KL_div of the chain (summary.jl:459-471)
+    yh = oracle.bond_yhat(B, L, R, xl, xr)
+    assert np.abs(yh - oracle.overlaps(cores, phi)).max() < 1e-13
+    mse, kld, acc = oracle.mse_loss_acc(cores, phi, ys)
+    assert abs(kld - oracle.loss_grad_KLD(B, L, R, xl, xr, counts)[0]) < 1e-12
+
+
+def test_truncation_rule(oracle):
+    P = np.array([1.0, 0.5, 1e-3, 1e-12, 1e-13, 0.0])
+    assert oracle.truncate_spectrum(P, 10, 1e-10) == 3
+    assert oracle.truncate_spectrum(P, 2, 1e-10) == 2
+    assert oracle.truncate_spectrum(P, 10, 0.0) == 5            # exact zeros satisfy err + 0 <= 0
+    assert oracle.truncate_spectrum(np.array([0.0, 0.0]), 5, 1e-10) == 1
+    # weight already discarded by maxdim counts towards the cutoff sum
+    P = np.array([1.0, 1e-3, 6e-11, 6e-11])
+    assert oracle.truncate_spectrum(P, 3, 1e-10) == 3
+    assert oracle.truncate_spectrum(P[:3], 3, 1e-10) == 2
+
+
+def test_decompose_reconstructs(oracle):
+    rng = np.random.default_rng(1)
+    d, cl, cr, C = 3, 4, 5, 2
+    B = rng.standard_normal((d * cl * d * cr, C))
+    for gl in (True, False):
+        a, b, S = oracle.decompose_bt(B, (cl, d, cr), gl, 100, 0.0)
+        full = np.einsum("asmc,mtb->btasc", a, b) if gl else np.einsum("asm,mtbc->btasc", a, b)
+        assert np.abs(full.reshape(-1, C) - B).max() < 1e-12
+        a, b, S = oracle.decompose_bt(B, (cl, d, cr), gl, 5, 1e-10)
+        assert len(S) == 5
+
+
+def test_sweep_decreases_loss_and_loop_equals_vectorised(oracle):
+    phi, ys, counts, cores = _problem(oracle)
+    rec, rec2 = [], []
+    new = oracle.fit_sweeps(cores, phi, counts, nsweeps=3, chi_max=10, eta=0.05, record=rec)
+    per = [np.mean([r["loss"] for r in rec if r["sweep"] == s]) for s in range(3)]
+    assert per[0] > per[1] > per[2]
+    assert abs(oracle._norm2_general(new) - 1.0) < 1e-12
+    oracle.fit_sweeps(cores, phi, counts, nsweeps=1, chi_max=10, eta=0.05, record=rec2, loop=True)
+    assert max(abs(a["loss"] - b["loss"]) for a, b in zip(rec, rec2)) < 1e-9
+    assert oracle.mse_loss_acc(new, phi, ys)[2] >= oracle.mse_loss_acc(cores, phi, ys)[2]
+
+
+def test_imputation_gram_equals_qr(oracle):
+    """orthogonalize!-based rho (MPS_methods.jl:110,152) == right-Gram formulation."""
+    phi, ys, counts, cores = _problem(oracle, N=60, T=8)
+    new = oracle.fit_sweeps(cores, phi, counts, nsweeps=2, chi_max=8, eta=0.05)
+    cls = oracle.expand_label_index(new)[0]
+    assert abs(oracle._norm2_general(cls) - 1.0) < 1e-12
+    d = phi.shape[2]
+    x = np.linspace(-0.5, 0.5, 8)
+    missing = [2, 3, 5]
+    cond = oracle.precondition(cls, oracle.encode(x, d), missing)
+    orth = oracle.orthogonalize_to_first(cond)
+    A = orth[0][0]
+    rho_qr = A @ A.T
+    G = np.ones((1, 1))
+    for k in range(len(cond) - 1, 0, -1):
+        G = np.einsum("asb,bc,xsc->ax", cond[k], G, cond[k])
+    rho_gram = np.einsum("sb,bc,tc->st", cond[0][0], G, cond[0][0])
+    assert np.abs(rho_qr - rho_gram).max() < 1e-12 * np.abs(rho_qr).max()
+    grid = oracle.make_grid()
+    assert len(grid) == 20001 and grid[0] == -1.0 and grid[-1] == 1.0
+    genc = oracle.encode(grid, d)
+    out, idx = oracle.impute_series(cls, x, missing, grid, genc, d)
+    assert np.all(out[[0, 1, 4, 6, 7]] == x[[0, 1, 4, 6, 7]]) and np.all(np.abs(out[missing]) <= 1)
+    u = [0.5, 0.5, 0.5]
+    out2, idx2 = oracle.impute_series(cls, x, missing, grid, genc, d, method="ITS", uniforms=u)
+    assert np.array_equal(idx, idx2)                        # ITS at u = 1/2 is the median
