@@ -86,6 +86,10 @@ struct mpst_ctx {
     size_t wbufcap = 0;
     double* colnorm = nullptr;  // [npad]
     int* perm = nullptr;        // [npad]
+    double* sub = nullptr;      // subspace-SVD workspace
+    size_t subcap = 0;
+    int* flags = nullptr;       // dataflow counters of the fused Jacobi sweep
+    size_t flagcap = 0;
     int* iscal = nullptr;       // device ints [16]
     int* hiscal = nullptr;      // pinned
     double* meta = nullptr;     // class offsets (int64) + loss normalisers, 256 doubles
