@@ -3,16 +3,18 @@
 // the hot bond GEMMs have their own fused kernels (krao_gemm.cu, bond_grad.cu).
 // CTA tile 64x64, K chunks of 16, 8 warps (4x2, warp tile 16x32), register-prefetched double buffering,
 // operand pitches == 4 (mod 16) doubles -> conflict-free fragment loads.
+#include <algorithm>
 #include "mpst_common.cuh"
 #include "dmma.cuh"
 
 namespace {
 constexpr int BM = 64, BN = 64, BK = 16, LDS = BK + 4;
 
-// A(i,k) = A[i*sai + k*sak],  B(k,j) = B[k*sbk + j*sbj]
+// A(i,k) = A[i*sai + k*sak],  B(k,j) = B[k*sbk + j*sbj].  blockIdx.z = K split: split z handles the K chunks
+// [z*kper, (z+1)*kper) and writes its partial product to C + z*cz (summed by the consumer in fixed order).
 __global__ void __launch_bounds__(256)
 dgemm_kernel(const double* __restrict__ A, int64_t sai, int64_t sak, const double* __restrict__ B, int64_t sbk,
-             int64_t sbj, double* __restrict__ C, int64_t ldc, int M, int N, int K) {
+             int64_t sbj, double* __restrict__ C, int64_t ldc, int M, int N, int K, int kper, int64_t cz) {
     __shared__ double As[2][BM][LDS];
     __shared__ double Bs[2][BN][LDS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -53,12 +55,15 @@ dgemm_kernel(const double* __restrict__ A, int64_t sai, int64_t sak, const doubl
     for (int a = 0; a < 2; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-    const int nk = (K + BK - 1) / BK;
-    load(0);
-    store(0);
+    const int nk_all = (K + BK - 1) / BK;
+    const int kc0 = blockIdx.z * kper;
+    const int nk = min(nk_all, kc0 + kper);
+    C += (int64_t)blockIdx.z * cz;
+    load(kc0);
+    store(kc0 & 1);
     __syncthreads();
     const int fr = lane >> 2, fc = lane & 3;
-    for (int kc = 0; kc < nk; kc++) {
+    for (int kc = kc0; kc < nk; kc++) {
         const int cur = kc & 1;
         if (kc + 1 < nk) load(kc + 1);
 #pragma unroll
@@ -97,8 +102,26 @@ int launch_dgemm(mpst_ctx* c, int ta, int tb, int M, int N, int K, const double*
     const int64_t sai = ta ? lda : 1, sak = ta ? 1 : lda;
     const int64_t sbk = tb ? ldb : 1, sbj = tb ? 1 : ldb;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-    dgemm_kernel<<<grid, 256, 0, c->stream>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K);
+    dgemm_kernel<<<grid, 256, 0, c->stream>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, (K + BK - 1) / BK, 0);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
+    return MPST_OK;
+}
+
+// split-K variant: `splits` partial products, partial z at C + z*M*N (ldc = M).  Returns the split count used.
+int launch_dgemm_splitk(mpst_ctx* c, int ta, int tb, int M, int N, int K, const double* A, int64_t lda, const double* B,
+                        int64_t ldb, double* Cparts, int max_splits, int* splits_out) {
+    const int64_t sai = ta ? lda : 1, sak = ta ? 1 : lda;
+    const int64_t sbk = tb ? ldb : 1, sbj = tb ? 1 : ldb;
+    const int nk = (K + BK - 1) / BK;
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int splits = std::max(1, std::min(std::min(max_splits, nk), (2 * c->sm_count) / std::max(tiles, 1)));
+    const int kper = (nk + splits - 1) / splits;
+    splits = (nk + kper - 1) / kper;
+    dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
+    dgemm_kernel<<<grid, 256, 0, c->stream>>>(A, sai, sak, B, sbk, sbj, Cparts, M, M, N, K, kper, (int64_t)M * N);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    *splits_out = splits;
     return MPST_OK;
 }

@@ -14,6 +14,7 @@
 // (fixed pairing and summation order), so replicated ranks stay bit-identical.
 // Truncation: NDTensors rule on P = sigma^2 (maxdim, then relative cutoff on the *sum* of
 // discarded weight), evaluated on the device.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include "mpst_common.cuh"
@@ -605,6 +606,7 @@ static int jacobi_sweeps_fused(mpst_ctx* c, int m, int n, int npad, int64_t ld, 
     int sweeps = 0;
     bool converged = false;
     std::string hist;
+    const auto t0 = std::chrono::steady_clock::now();
     for (; sweeps < 60 && !converged; sweeps++) {
         if (fixed && sweeps >= fixed) { converged = true; break; }
         if (partial) {
@@ -625,7 +627,8 @@ static int jacobi_sweeps_fused(mpst_ctx* c, int m, int n, int npad, int64_t ld, 
         if (sweeps < 64) { char b[32]; snprintf(b, sizeof b, " %.2e", c->hscal[8]); hist += b; }
         if (!(c->hscal[8] == c->hscal[8])) break;
     }
-    if (getenv("MPST_SVD_DEBUG")) fprintf(stderr, "[svd fused] m=%d n=%d R=%d sweeps=%d:%s\n", m, n, R, sweeps, hist.c_str());
+    if (getenv("MPST_SVD_DEBUG")) fprintf(stderr, "[svd fused] m=%d n=%d R=%d sweeps=%d t=%.3f ms:%s\n", m, n, R, sweeps,
+                                          1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), hist.c_str());
     if (!converged) {
         char b[160];
         snprintf(b, sizeof b, "svd: Jacobi did not converge (m=%d n=%d) max-offdiag per sweep:", m, n);

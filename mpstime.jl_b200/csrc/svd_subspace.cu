@@ -15,12 +15,15 @@
 // (or a Cholesky pivot breaks down: numerically rank-deficient block) the caller falls back to the exact
 // full Jacobi SVD (svd_jacobi.cu), so the result never depends on the spectrum being friendly.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include "mpst_common.cuh"
 
 int launch_dgemm(mpst_ctx* c, int ta, int tb, int M, int N, int K, const double* A, int64_t lda, const double* B,
                  int64_t ldb, double* C, int64_t ldc);
+int launch_dgemm_splitk(mpst_ctx* c, int ta, int tb, int M, int N, int K, const double* A, int64_t lda, const double* B,
+                        int64_t ldb, double* Cparts, int max_splits, int* splits_out);
 
 namespace {
 
@@ -39,132 +42,148 @@ __global__ void rand_init_kernel(double* __restrict__ Q, int n, int p, int64_t l
     Q[i + ld * j] = hash_unit(seed + (uint64_t)e * 0x632BE59BD9B4E019ull);
 }
 
-// G (p x p, symmetric positive definite) = L L^T;  Rinv = (L^T)^-1 (upper, column-major p x p).
-// Single CTA.  status[0] |= 1 when a pivot is not safely positive (caller falls back).
+// G = sum of `splits` partial Gram matrices (p x p, symmetric positive definite) = L L^T;
+// Rinv = (L^T)^-1 = (L^-1)^T (upper, column-major p x p).  Single CTA, one right-looking pass that factors
+// column k and immediately eliminates it from the running inverse (forward substitution on the identity),
+// two block barriers per column, every update a 2-D thread-parallel rank-1 update in shared memory.
+// status[0] |= 1 when a pivot is not safely positive (caller falls back to the exact SVD).
 __global__ void __launch_bounds__(256)
-chol_inv_kernel(const double* __restrict__ G, int p, double* __restrict__ Rinv, int* __restrict__ status) {
+chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restrict__ Rinv, int* __restrict__ status) {
     extern __shared__ double sm[];
     const int ld = p + 1;
-    double* A = sm;                                    // [p][ld], lower triangle used
-    __shared__ double s_piv;
+    double* A = sm;                                    // [p][ld]: lower triangle -> L
+    double* X = sm + (size_t)p * ld;                   // [p][ld]: running B (rows > k) / finished X = L^-1 (rows <= k)
     __shared__ int s_bad;
-    const int tid = threadIdx.x;
-    double tr = 0.0;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     for (int e = tid; e < p * p; e += 256) {
-        const int i = e / p, j = e % p;
-        A[i * ld + j] = G[i + (size_t)p * j];
+        const int i = e % p, j = e / p;
+        double v = 0.0;
+        for (int z = 0; z < splits; z++) v += G[(size_t)z * p * p + e];
+        A[i * ld + j] = v;
+        X[i * ld + j] = (i == j) ? 1.0 : 0.0;
     }
     if (tid == 0) s_bad = 0;
     __syncthreads();
+    double tr = 0.0;
     for (int i = 0; i < p; i++) tr = fmax(tr, A[i * ld + i]);
     const double tiny = 1e-13 * tr;                    // kappa(G) beyond ~1e13: CholeskyQR no longer trustworthy
-    for (int j = 0; j < p; j++) {
-        if (tid == 0) {
-            const double d = A[j * ld + j];
-            if (!(d > tiny)) s_bad = 1;
-            s_piv = sqrt(fmax(d, tiny));
-        }
+    for (int k = 0; k < p; k++) {
+        const double dk = A[k * ld + k];
+        if (tid == 0 && !(dk > tiny)) s_bad = 1;
+        const double inv = rsqrt(fmax(dk, tiny));      // 1 / l_kk
+        __syncthreads();                               // everybody has read the pivot
+        // scale column k of L (rows >= k) and finish row k of X (columns <= k)
+        for (int i = k + tid; i < p; i += 256) A[i * ld + k] *= inv;      // A[k][k] = dk/sqrt(dk) = l_kk
+        for (int j = tid; j <= k; j += 256) X[k * ld + j] *= inv;
         __syncthreads();
-        const double ljj = s_piv;
-        for (int i = j + tid; i < p; i += 256) A[i * ld + j] = (i == j) ? ljj : A[i * ld + j] / ljj;
-        __syncthreads();
-        // trailing update of the lower triangle: A[i][l] -= A[i][j] * A[l][j],  j < l <= i
-        const int nt = p - j - 1;
-        for (int e = tid; e < nt * nt; e += 256) {
-            const int i = j + 1 + e / nt, l = j + 1 + e % nt;
-            if (l <= i) A[i * ld + l] -= A[i * ld + j] * A[l * ld + j];
+        // rank-1 updates with column k:  A[i][l] -= L[i][k] L[l][k] (k < l <= i),  B[i][j] -= L[i][k] X[k][j] (j <= k < i)
+        for (int i = k + 1 + ty; i < p; i += 16) {
+            const double lik = A[i * ld + k];
+            for (int l = k + 1 + tx; l <= i; l += 16) A[i * ld + l] -= lik * A[l * ld + k];
+            for (int j = tx; j <= k; j += 16) X[i * ld + j] -= lik * X[k * ld + j];
         }
+        // no barrier needed before the next pivot read: A[k+1][k+1] is written by its owner above and the
+        // barrier at the top of the next iteration orders it (pivot is read before that barrier -> add one)
         __syncthreads();
     }
-    // X = L^-1 (lower); thread j owns column j and keeps it in the unused upper triangle: X[i][j] -> A[j][i]
-    // (i > j); the diagonal 1/l_jj goes to xd[].  Rinv(l, i) = X(i, l): Rinv[j + p*i] = X[i][j].
-    double* xd = sm + (size_t)p * ld;
-    for (int j = tid; j < p; j += 256) {
-        const double xjj = 1.0 / A[j * ld + j];
-        xd[j] = xjj;
-        for (int i = j + 1; i < p; i++) {
-            double s = A[i * ld + j] * xjj;
-            for (int l = j + 1; l < i; l++) s += A[i * ld + l] * A[j * ld + l];
-            A[j * ld + i] = -s / A[i * ld + i];
-        }
-    }
-    __syncthreads();
     for (int e = tid; e < p * p; e += 256) {
-        const int jj = e % p, i = e / p;                       // Rinv[jj + p*i]
-        Rinv[e] = (i > jj) ? A[jj * ld + i] : (i == jj ? xd[jj] : 0.0);
+        const int jj = e % p, i = e / p;               // Rinv[jj + p*i] = X[i][jj]  (i >= jj)
+        Rinv[e] = (i >= jj) ? X[i * ld + jj] : 0.0;
     }
     if (tid == 0 && s_bad) atomicOr(status, 1);
 }
 
-// Eigen-decomposition of a symmetric p x p matrix (p even) by cyclic two-sided Jacobi in shared memory.
-// p/2 disjoint rotations per round, 8 threads each.  W: column-major eigenvectors, ev: eigenvalues (unsorted).
-__global__ void __launch_bounds__(1024)
-sym_eig_kernel(const double* __restrict__ H, int p, double* __restrict__ W, double* __restrict__ ev,
+// Eigen-decomposition of a symmetric q x q matrix (embedded in an even order p >= q) by cyclic two-sided
+// Jacobi in shared memory, one CTA.  Per round the p/2 disjoint rotations are computed first, then every
+// 2x2 block (pair I, pair J), I <= J, of A is transformed once with both rotations (B' = R_I^T B R_J) and
+// mirrored, and V's column pairs are rotated: one pass over A (upper half) and V per round, two barriers.
+// W: column-major eigenvectors, ev: eigenvalues (unsorted).  status[1] = sweeps used.
+__global__ void __launch_bounds__(512)
+sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* __restrict__ W, double* __restrict__ ev,
                int* __restrict__ status) {
     extern __shared__ double sm[];
-    const int ld = p + 1;
+    const int ld = p + 1, hp = p / 2;
     double* A = sm;
     double* V = sm + (size_t)p * ld;
+    double* rc = V + (size_t)p * ld;                   // [hp] cos
+    double* rs = rc + hp;                              // [hp] sin
+    int* rp = reinterpret_cast<int*>(rs + hp);         // [hp] p index, [hp] q index
+    int* rq = rp + hp;
     __shared__ int any_rot;
+    __shared__ unsigned long long s_maxaa;
     const int tid = threadIdx.x, nthr = blockDim.x;
     for (int e = tid; e < p * p; e += nthr) {
         const int i = e / p, j = e % p;
-        A[i * ld + j] = 0.5 * (H[i + (size_t)p * j] + H[j + (size_t)p * i]);
+        double v = 0.0;
+        if (i < q && j < q)
+            for (int z = 0; z < splits; z++) v += H[(size_t)z * q * q + i + (size_t)q * j] + H[(size_t)z * q * q + j + (size_t)q * i];
+        A[i * ld + j] = 0.5 * v;
         V[i * ld + j] = (i == j) ? 1.0 : 0.0;
     }
     __syncthreads();
     double tr = 0.0;
     for (int i = 0; i < p; i++) tr += A[i * ld + i];
-    const double floor_abs = 1e-17 * tr;
-    const int k = tid >> 3, l8 = tid & 7;
-    const bool active = k < p / 2;
+    // H is a Gram matrix: its entries carry absolute errors ~eps*trace, so couplings below a few eps*trace are
+    // noise (rotating them never terminates); the eigenvalues are resolved to that absolute accuracy anyway.
+    const double floor_abs = 1e-15 * tr;
     int sweep = 0;
     for (; sweep < 60; sweep++) {
-        if (tid == 0) any_rot = 0;
+        if (tid == 0) { any_rot = 0; s_maxaa = 0ull; }
         __syncthreads();
         for (int rd = 0; rd < p - 1; rd++) {
-            int pp = 0, qq = 1;
-            double c = 1.0, s = 0.0;
-            if (active) {
+            if (tid < hp) {
+                const int k = tid;
                 int a, b;
                 if (k == 0) { a = p - 1; b = rd; }
                 else { a = (rd + k) % (p - 1); b = (rd - k + (p - 1)) % (p - 1); }
-                pp = min(a, b); qq = max(a, b);
+                const int pp = min(a, b), qq = max(a, b);
                 const double app = A[pp * ld + pp], aqq = A[qq * ld + qq], apq = A[pp * ld + qq];
                 const double aa = fabs(apq);
+                double c = 1.0, sn = 0.0;
                 if (aa > floor_abs && aa * aa > 1e-30 * fabs(app * aqq)) {
                     const double zeta = aqq - app, beta = 2.0 * apq;
                     const double t = (zeta >= 0.0 ? beta : -beta) / (fabs(zeta) + sqrt(zeta * zeta + beta * beta));
                     c = 1.0 / sqrt(1.0 + t * t);
-                    s = t * c;
-                    if (l8 == 0) any_rot = 1;
+                    sn = t * c;
+                    any_rot = 1;
+                    atomicMax(&s_maxaa, (unsigned long long)__double_as_longlong(aa));
                 }
-            }
-            __syncwarp();
-            if (active) {
-                for (int r = l8; r < p; r += 8) {
-                    const double x = A[r * ld + pp], y = A[r * ld + qq];
-                    A[r * ld + pp] = c * x - s * y;
-                    A[r * ld + qq] = s * x + c * y;
-                    const double vx = V[r * ld + pp], vy = V[r * ld + qq];
-                    V[r * ld + pp] = c * vx - s * vy;
-                    V[r * ld + qq] = s * vx + c * vy;
-                }
+                rc[k] = c; rs[k] = sn; rp[k] = pp; rq[k] = qq;
             }
             __syncthreads();
-            if (active) {
-                for (int cc = l8; cc < p; cc += 8) {
-                    const double x = A[pp * ld + cc], y = A[qq * ld + cc];
-                    A[pp * ld + cc] = c * x - s * y;
-                    A[qq * ld + cc] = s * x + c * y;
-                }
+            // A blocks (I <= J), mirrored
+            for (int e = tid; e < hp * hp; e += nthr) {
+                const int I = e / hp, J = e - I * hp;
+                if (I > J) continue;
+                const int pi = rp[I], qi = rq[I], pj = rp[J], qj = rq[J];
+                const double ci = rc[I], si = rs[I], cj = rc[J], sj = rs[J];
+                const double b11 = A[pi * ld + pj], b12 = A[pi * ld + qj], b21 = A[qi * ld + pj], b22 = A[qi * ld + qj];
+                // columns: B R_J
+                const double t11 = cj * b11 - sj * b12, t12 = sj * b11 + cj * b12;
+                const double t21 = cj * b21 - sj * b22, t22 = sj * b21 + cj * b22;
+                // rows: R_I^T (.)
+                const double n11 = ci * t11 - si * t21, n12 = ci * t12 - si * t22;
+                const double n21 = si * t11 + ci * t21, n22 = si * t12 + ci * t22;
+                A[pi * ld + pj] = n11; A[pi * ld + qj] = n12; A[qi * ld + pj] = n21; A[qi * ld + qj] = n22;
+                if (I != J) { A[pj * ld + pi] = n11; A[qj * ld + pi] = n12; A[pj * ld + qi] = n21; A[qj * ld + qi] = n22; }
+            }
+            // V column pairs
+            for (int e = tid; e < hp * p; e += nthr) {
+                const int k = e / p, r = e - k * p;
+                const int pp = rp[k], qq = rq[k];
+                const double c = rc[k], sn = rs[k];
+                const double vx = V[r * ld + pp], vy = V[r * ld + qq];
+                V[r * ld + pp] = c * vx - sn * vy;
+                V[r * ld + qq] = sn * vx + c * vy;
             }
             __syncthreads();
         }
-        if (!any_rot) break;
+        // quadratic convergence: a sweep whose largest rotated entry was <= 1e-9*trace leaves <= ~1e-18*trace
+        if (!any_rot || __longlong_as_double((long long)s_maxaa) <= 1e-9 * tr) break;
         __syncthreads();
     }
     if (tid == 0 && sweep >= 60) atomicOr(status, 2);
+    if (tid == 0) status[1] = sweep;
     for (int e = tid; e < p * p; e += nthr) {
         const int i = e / p, j = e % p;
         W[i + (size_t)p * j] = V[i * ld + j];
@@ -247,29 +266,60 @@ residual_kernel(const double* __restrict__ T2, const double* __restrict__ Vk, co
         atomicMax(out_bits, (unsigned long long)__double_as_longlong(rel));
     }
 }
+// scale the columns of Vk (n x k): Vk[:, i] *= 1/sqrt(P_i)   (wide Gram path: v_i = M^T u_i / sigma_i)
+__global__ void scale_cols_kernel(double* __restrict__ Vk, int n, const double* __restrict__ Psorted,
+                                  const int* __restrict__ iscal) {
+    const int chi = iscal[0];
+    const int64_t tot = (int64_t)n * chi;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / n);
+        Vk[e] *= rsqrt(fmax(Psorted[i], 1e-300));
+    }
+}
+// Uk[:, i] *= sqrt(P_i)   (wide Gram path: moving core = U_k Sigma_k)
+__global__ void scale_cols_sqrt_kernel(double* __restrict__ Uk, int m, const double* __restrict__ Psorted,
+                                       const int* __restrict__ iscal) {
+    const int chi = iscal[0];
+    const int64_t tot = (int64_t)m * chi;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x)
+        Uk[e] *= sqrt(fmax(Psorted[(int)(e / m)], 0.0));
+}
 }  // namespace
 
 // M: column-major m x n (leading dimension ldm) on the device, already scaled.  trace_dev: ||M||_F^2 on the
 // device or nullptr (== 1).  On success *done = true and the cores are written; *done = false means
 // "not applicable / not converged": the caller must run the full Jacobi SVD.
+// Three modes, all ending in the single-CTA symmetric eigen-solver on a matrix of order <= 112:
+//   tall-Gram  (n <= 112)          : H = M^T M,  V = eigenvectors, U S = M V
+//   wide-Gram  (m <= 112, m < n)   : H = M M^T,  U = eigenvectors, V = M^T U S^-1   (kept sigma >= 1e-5 sigma_1)
+//   subspace   (otherwise)         : block subspace iteration, H = (M Q)^T (M Q)
+// Working with sigma^2 resolves weights down to eps*sigma_1^2, so these paths are used only when the
+// truncation cutoff is >= 1e-12 (the reference default is 1e-10); smaller cutoffs take the exact Jacobi.
 int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n, int C, int chi_max, double cutoff,
                         const double* trace_dev, double* label_core, double* ortho_core, int* chi_new,
                         double* sigma_host, bool* done) {
     *done = false;
-    const int k = chi_max;
-    // subspace dimension: 2k+16, capped at 112 (two p x (p+1) matrices must fit the 227 KB of shared memory of
-    // the single-CTA Rayleigh-Ritz eigen-solver); at least 32 vectors of oversampling or the path is not taken
-    const int p = std::min((int)round_up(2 * k + 16, 16), 112);
-    if (getenv("MPST_SVD_NOSUB")) return MPST_OK;
-    if (p < k + 32 || n < p + 32 || m < p) return MPST_OK;            // small / wide problems: full Jacobi
-    const size_t need = (size_t)2 * n * p + (size_t)2 * m * p + 4 * (size_t)p * p + (size_t)n * k + (size_t)m * k + 4 * p + 64;
+    if (getenv("MPST_SVD_NOSUB") || cutoff < 1e-12) return MPST_OK;
+    const int k = std::min(chi_max, std::min(m, n));
+    const int PMAX = 112, MAXSPLIT = 16;
+    int mode;                                                          // 0 tall-Gram, 1 wide-Gram, 2 subspace
+    int p;
+    if (n <= PMAX) { mode = 0; p = n + (n & 1); }
+    else if (m <= PMAX && m < n) { mode = 1; p = m + (m & 1); }
+    else {
+        mode = 2;
+        p = std::min((int)round_up(2 * k + 16, 16), PMAX);
+        if (p < k + 32 || n <= p || m < p) return MPST_OK;            // too little oversampling: full Jacobi
+    }
+    const size_t need = (size_t)2 * n * p + (size_t)2 * m * p + (size_t)(MAXSPLIT + 3) * p * p + (size_t)n * k +
+                        (size_t)m * k + 4 * p + 64;
     TRY(ensure_buf(c, &c->sub, &c->subcap, need));
     double* Qa = c->sub;
     double* Qb = Qa + (size_t)n * p;
     double* Za = Qb + (size_t)n * p;
     double* Zb = Za + (size_t)m * p;
-    double* Gm = Zb + (size_t)m * p;
-    double* Ri = Gm + (size_t)p * p;
+    double* Gm = Zb + (size_t)m * p;                                   // MAXSPLIT partial Gram matrices
+    double* Ri = Gm + (size_t)MAXSPLIT * p * p;
     double* Wm = Ri + (size_t)p * p;
     double* Wk = Wm + (size_t)p * p;
     double* T2 = Wk + (size_t)p * p;                                   // n x k
@@ -277,16 +327,74 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     double* ev = Uk + (size_t)m * k;                                   // p, then Psorted p
     int* status = c->iscal + 8;
     unsigned long long* resbits = reinterpret_cast<unsigned long long*>(c->scal + 10);
-    const size_t chol_smem = sizeof(double) * ((size_t)p * (p + 1) + p);
-    const size_t eig_smem = 2 * sizeof(double) * (size_t)p * (p + 1);
+    const size_t chol_smem = 2 * sizeof(double) * (size_t)p * (p + 1);
+    const size_t eig_smem = 2 * sizeof(double) * (size_t)p * (p + 1) + sizeof(double) * p + sizeof(int) * p + 16;
     CUDA_TRY(c, cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
     CUDA_TRY(c, cudaFuncSetAttribute(sym_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem));
     CUDA_TRY(c, cudaMemsetAsync(status, 0, sizeof(int), c->stream));
+    const bool dbg = getenv("MPST_SVD_DEBUG") != nullptr;
+    if (dbg) cudaStreamSynchronize(c->stream);
+    const auto t0 = std::chrono::steady_clock::now();
+    const unsigned eig_threads = p >= 64 ? 512u : 256u;
 
-    // X (rows x p, ld = rows) -> orthonormal columns in `out`; `tmp` is scratch of the same size
+    auto finish = [&](const char* what, int iters, double res) -> int {
+        *chi_new = c->hiscal[0];
+        scatter_label_kernel<<<2 * c->sm_count, 256, 0, c->stream>>>(Uk, m, m / C, c->iscal, label_core);
+        c->launches++;
+        CUDA_TRY(c, cudaGetLastError());
+        if (sigma_host) {
+            std::vector<double> tmp(*chi_new);
+            CUDA_TRY(c, cudaMemcpy(tmp.data(), ev + p, sizeof(double) * (*chi_new), cudaMemcpyDeviceToHost));
+            for (int q = 0; q < *chi_new; q++) sigma_host[q] = sqrt(tmp[q]);
+        }
+        if (dbg) {
+            cudaStreamSynchronize(c->stream);
+            fprintf(stderr, "[svd %s] m=%d n=%d p=%d iters=%d chi=%d residual=%.2e eigsweeps=%d t=%.3f ms\n", what, m, n, p, iters, *chi_new, res, c->hiscal[9],
+                    1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        }
+        *done = true;
+        return MPST_OK;
+    };
+
+    if (mode != 2) {
+        // ---- Gram paths: one small symmetric eigenproblem, no iteration ----
+        const int q = mode == 0 ? n : m;                               // order of H (p = q rounded up to even)
+        int splits = 1;
+        if (mode == 0) TRY(launch_dgemm_splitk(c, 1, 0, q, q, m, M, ldm, M, ldm, Gm, MAXSPLIT, &splits));   // M^T M
+        else TRY(launch_dgemm_splitk(c, 0, 1, q, q, n, M, ldm, M, ldm, Gm, MAXSPLIT, &splits));            // M M^T
+        sym_eig_kernel<<<1, eig_threads, eig_smem, c->stream>>>(Gm, splits, q, p, Wm, ev, status);
+        ritz_trunc_kernel<<<1, 256, 0, c->stream>>>(ev, p, q, trace_dev, chi_max, cutoff, c->perm, ev + p, c->iscal);
+        gather_cols_kernel<<<(p * k + 255) / 256, 256, 0, c->stream>>>(Wm, p, c->perm, k, Wk);
+        c->launches += 3;
+        if (mode == 0) {
+            // V_k = W_k (rows < n), U_k S_k = M V_k
+            CUDA_TRY(c, cudaMemcpy2DAsync(ortho_core, sizeof(double) * n, Wk, sizeof(double) * p, sizeof(double) * n, k,
+                                          cudaMemcpyDeviceToDevice, c->stream));
+            TRY(launch_dgemm(c, 0, 0, m, k, n, M, ldm, ortho_core, n, Uk, m));
+        } else {
+            // U_k = W_k (rows < m);  V_k = M^T U_k / sigma;  U_k S_k = U_k * sigma
+            CUDA_TRY(c, cudaMemcpy2DAsync(Uk, sizeof(double) * m, Wk, sizeof(double) * p, sizeof(double) * m, k,
+                                          cudaMemcpyDeviceToDevice, c->stream));
+            TRY(launch_dgemm(c, 1, 0, n, k, m, M, ldm, Uk, m, ortho_core, n));
+        }
+        CUDA_TRY(c, cudaMemcpyAsync(c->hiscal, c->iscal, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->hiscal + 8, status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        if (c->hiscal[8] != 0) return MPST_OK;
+        if (mode == 1) {
+            scale_cols_kernel<<<2 * c->sm_count, 256, 0, c->stream>>>(ortho_core, n, ev + p, c->iscal);
+            scale_cols_sqrt_kernel<<<2 * c->sm_count, 256, 0, c->stream>>>(Uk, m, ev + p, c->iscal);
+            c->launches += 2;
+        }
+        return finish(mode == 0 ? "gram-tall" : "gram-wide", 0, 0.0);
+    }
+
+    // ---- subspace iteration ----
+    // X (rows x p, ld = rows) -> orthonormal columns in `out`
     auto cholqr = [&](double* X, double* out, int rows) -> int {
-        TRY(launch_dgemm(c, 1, 0, p, p, rows, X, rows, X, rows, Gm, p));
-        chol_inv_kernel<<<1, 256, chol_smem, c->stream>>>(Gm, p, Ri, status);
+        int splits = 1;
+        TRY(launch_dgemm_splitk(c, 1, 0, p, p, rows, X, rows, X, rows, Gm, MAXSPLIT, &splits));
+        chol_inv_kernel<<<1, 256, chol_smem, c->stream>>>(Gm, splits, p, Ri, status);
         c->launches++;
         TRY(launch_dgemm(c, 0, 0, rows, p, p, X, rows, Ri, p, out, rows));
         return MPST_OK;
@@ -312,13 +420,14 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         TRY(cholqr(Qa, Qb, n));                                                    // second pass: orthonormal to rounding
         CUDA_TRY(c, cudaMemcpyAsync(Qa, Qb, sizeof(double) * (size_t)n * p, cudaMemcpyDeviceToDevice, c->stream));
         // Rayleigh-Ritz
+        int splits = 1;
         TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, Qa, n, Za, m));                // Z = M Q
-        TRY(launch_dgemm(c, 1, 0, p, p, m, Za, m, Za, m, Gm, p));                 // H = Z^T Z
-        sym_eig_kernel<<<1, (unsigned)round_up((p / 2) * 8, 32), eig_smem, c->stream>>>(Gm, p, Wm, ev, status);
+        TRY(launch_dgemm_splitk(c, 1, 0, p, p, m, Za, m, Za, m, Gm, MAXSPLIT, &splits));   // H = Z^T Z
+        sym_eig_kernel<<<1, eig_threads, eig_smem, c->stream>>>(Gm, splits, p, p, Wm, ev, status);
         ritz_trunc_kernel<<<1, 256, 0, c->stream>>>(ev, p, n, trace_dev, chi_max, cutoff, c->perm, ev + p, c->iscal);
         gather_cols_kernel<<<(p * k + 255) / 256, 256, 0, c->stream>>>(Wm, p, c->perm, k, Wk);
         c->launches += 3;
-        TRY(launch_dgemm(c, 0, 0, n, k, p, Qa, n, Wk, p, ortho_core, n));         // V_k = Q W_k  (all k columns; chi_new <= k used)
+        TRY(launch_dgemm(c, 0, 0, n, k, p, Qa, n, Wk, p, ortho_core, n));         // V_k = Q W_k
         TRY(launch_dgemm(c, 0, 0, m, k, p, Za, m, Wk, p, Uk, m));                 // U_k S_k = Z W_k
         // residual of the kept Ritz pairs: M^T (M v_i) - sigma_i^2 v_i
         TRY(launch_dgemm(c, 1, 0, n, k, m, M, ldm, Uk, m, T2, n));
@@ -327,26 +436,17 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         c->launches++;
         CUDA_TRY(c, cudaGetLastError());
         CUDA_TRY(c, cudaMemcpyAsync(c->hiscal, c->iscal, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaMemcpyAsync(c->hiscal + 8, status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->hiscal + 8, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(c->hscal + 10, resbits, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         const double res = c->hscal[10];
-        if (getenv("MPST_SVD_DEBUG"))
-            fprintf(stderr, "[svd subspace] m=%d n=%d p=%d iters=%d chi=%d status=%d residual=%.2e\n", m, n, p, iters_done,
-                    c->hiscal[0], c->hiscal[8], res);
-        if (c->hiscal[8] != 0 || !(res == res)) return MPST_OK;                    // breakdown: full Jacobi
-        if (res > (round == 0 ? 1e-5 : 1e-10)) return MPST_OK;                     // spectrum too flat: full Jacobi
-        if (res <= 5e-14) {
-            *chi_new = c->hiscal[0];
-            scatter_label_kernel<<<2 * c->sm_count, 256, 0, c->stream>>>(Uk, m, m / C, c->iscal, label_core);
-            c->launches++;
-            CUDA_TRY(c, cudaGetLastError());
-            if (sigma_host) {
-                std::vector<double> tmp(*chi_new);
-                CUDA_TRY(c, cudaMemcpy(tmp.data(), ev + p, sizeof(double) * (*chi_new), cudaMemcpyDeviceToHost));
-                for (int q = 0; q < *chi_new; q++) sigma_host[q] = sqrt(tmp[q]);
-            }
-            *done = true;
+        if (c->hiscal[8] != 0 || !(res == res)) {
+            if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d breakdown status=%d -> full Jacobi\n", m, n, c->hiscal[8]);
+            return MPST_OK;
+        }
+        if (res <= 5e-14) return finish("subspace", iters_done, res);
+        if (res > (round == 0 ? 1e-5 : 1e-10)) {                                   // spectrum too flat: full Jacobi
+            if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d residual %.2e after %d its -> full Jacobi\n", m, n, res, iters_done);
             return MPST_OK;
         }
     }
