@@ -205,8 +205,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="override samples per GPU (debug)")
-    ap.add_argument("--t", type=int, default=0, help="override series length (debug)")
+    ap.add_argument("--samples-per-gpu", dest="n", type=int, default=0, help="override samples per GPU (debug)")
+    ap.add_argument("--series-length", dest="t", type=int, default=0, help="override series length (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -278,6 +278,9 @@ def main():
     e2e_s = max_over_ranks(td, local, time.time() - t0)
     e2e = sample_bonds / e2e_s
 
+    if td is not None:
+        td.barrier(device_ids=[local])
+        td.destroy_process_group()
     if rank != 0:
         return
     gk_ms, gk_n, gk_fl = prof["grad_kernel"]

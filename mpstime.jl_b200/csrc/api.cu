@@ -451,15 +451,42 @@ int mpst_build_env(mpst_ctx* c, int going_left) {
 }
 
 // ---- loss + gradient on device operands ([Npad][.] row-major, B/G as [C][Dl*Dr]) -------------
+// fac_l / fac_r (optional): the two bond cores when B == W_l * W_r exactly (first optimiser iteration).  Then
+// yhat_ic = (P_i W_l) . (W_r^c Q_i) is evaluated from the factors -- 4*d*chi^2 flops per sample instead of the
+// 2*d^2*chi^2 of the dense contraction; identical up to summation order.
 static int loss_grad_device(mpst_ctx* c, const double* phl, const double* phr, const double* L, const double* R,
                             int chi_l, int chi_r, const double* B, double* G, int loss_kind, int train_sep,
-                            double* loss_dev, int64_t* coff_dev, double* denom_dev) {
+                            double* loss_dev, int64_t* coff_dev, double* denom_dev, const Core* fac_l = nullptr,
+                            const Core* fac_r = nullptr) {
     const int d = c->d, C = c->C;
     const int Dl = d * chi_l, Dr = d * chi_r;
     const size_t D = (size_t)Dl * Dr;
-    // forward: yhat[c][i] = <B_c, phi~_i>  (dense: Z = P * B_c in row blocks, then the Q-weighted row sum)
+    // forward: yhat[c][i] = <B_c, phi~_i>
     {
         ProfScope ps(c, MPST_T_FWD);
+        if (fac_l && fac_r && !getenv("MPST_DENSE_FWD")) {
+            // factorised: a = P W_l (N x chi_m [per class if W_l carries the label]), b = Q W_r, yhat = a . b
+            const int chi_m = fac_l->chi_r;
+            const bool lab_l = fac_l->has_label != 0;
+            const size_t csz_l = (size_t)d * fac_l->chi_l * fac_l->chi_r, csz_r = (size_t)d * fac_r->chi_l * fac_r->chi_r;
+            const int nbuf = (loss_kind == MPST_LOSS_KLD) ? 1 : C;          // KLD: disjoint row ranges share one buffer
+            TRY(ensure_buf(c, &c->Z, &c->Zcap, (size_t)c->Npad * chi_m * (nbuf + 1)));
+            double* Ab = c->Z;                                               // unlabelled side
+            double* Lb = c->Z + (size_t)c->Npad * chi_m;                     // labelled side, nbuf buffers
+            if (lab_l) TRY(launch_krao_gemm_rows(c, phr, R, fac_r->dev, Ab, 0, c->N, d, chi_r, chi_m, Dr, chi_m));
+            else TRY(launch_krao_gemm_rows(c, phl, L, fac_l->dev, Ab, 0, c->N, d, chi_l, chi_m, Dl, chi_m));
+            for (int cls = 0; cls < C; cls++) {
+                const int64_t b0 = loss_kind == MPST_LOSS_KLD ? c->class_off[cls] : 0;
+                const int64_t b1 = loss_kind == MPST_LOSS_KLD ? c->class_off[cls + 1] : c->N;
+                double* out = Lb + (size_t)(nbuf == 1 ? 0 : cls) * c->Npad * chi_m;
+                if (lab_l) TRY(launch_krao_gemm_rows(c, phl, L, fac_l->dev + cls * csz_l, out, b0, b1, d, chi_l, chi_m, Dl, chi_m));
+                else TRY(launch_krao_gemm_rows(c, phr, R, fac_r->dev + cls * csz_r, out, b0, b1, d, chi_r, chi_m, Dr, chi_m));
+                TRY(launch_rowdot(c, Ab, chi_m, out, chi_m, b0, b1, chi_m, c->yhat + (size_t)cls * c->Npad));
+            }
+            c->prof_work[MPST_T_FWD] -= 2.0 * (loss_kind == MPST_LOSS_KLD ? (double)c->N : (double)c->N * C) * (double)D;
+            c->prof_work[MPST_T_FWD] += 2.0 * (double)c->N * chi_m * ((double)(lab_l ? Dr : Dl) + (double)(lab_l ? Dl : Dr) * (loss_kind == MPST_LOSS_KLD ? 1 : C));
+        } else {
+        // dense: Z = P * B_c in row blocks, then the Q-weighted row sum
         const int64_t SB = std::max<int64_t>(MPST_TILE, ((int64_t)(96 << 20) / (8 * (int64_t)Dr)) / MPST_TILE * MPST_TILE);
         TRY(ensure_buf(c, &c->Z, &c->Zcap, (size_t)(SB + 2 * MPST_TILE) * Dr));
         for (int cls = 0; cls < C; cls++) {
@@ -473,6 +500,7 @@ static int loss_grad_device(mpst_ctx* c, const double* phl, const double* phr, c
                 TRY(launch_rowdot_q(c, c->Z, Dr, phr, R, rb, re, d, chi_r, c->yhat + (size_t)cls * c->Npad));
                 rb = re;
             }
+        }
         }
         TRY(launch_loss_w(c, loss_kind, coff_dev, denom_dev, loss_dev));
     }
@@ -561,7 +589,13 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         TRY(launch_scale_dev(c, c->B, D * C, s_bn2));
     }
     for (int it = 0; it < o->update_iters; it++) {
-        TRY(loss_grad_device(c, phl, phr, L, R, chi_l, chi_r, c->B, c->G, o->loss_kind, o->train_sep, s_loss, coff_dev, denom_dev));
+        const bool factored = it == 0 && !o->rescale_before;
+        if (factored) {                                       // weights as [p][m] resp. [q][m]
+            TRY(core_orient(c, l, ORIENT_LEFT));
+            TRY(core_orient(c, r, ORIENT_RIGHT));
+        }
+        TRY(loss_grad_device(c, phl, phr, L, R, chi_l, chi_r, c->B, c->G, o->loss_kind, o->train_sep, s_loss, coff_dev, denom_dev,
+                             factored ? &kl : nullptr, factored ? &kr : nullptr));
         TRY(allreduce_sum(c, c->G, D * C + 1));
         ProfScope ps(c, MPST_T_UPDATE);
         TRY(launch_sumsq(c, c->G, D * C, s_gn2));
