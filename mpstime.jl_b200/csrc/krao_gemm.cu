@@ -160,6 +160,7 @@ int launch_krao_gemm_rows(mpst_ctx* c, const double* x, const double* E, const d
         if (n_out <= 8) return launch_cfg<128, 8, 8, 1>(ARGS);
         if (n_out <= 16) return launch_cfg<128, 16, 8, 1>(ARGS);
         if (n_out <= 32) return launch_cfg<128, 32, 8, 1>(ARGS);
+        if (n_out <= 48) return launch_cfg<128, 48, 4, 2>(ARGS);       // chi = 40 (config B): 17% padding instead of 37%
         if (n_out <= 64) return launch_cfg<128, 64, 4, 2>(ARGS);
         return launch_cfg<128, 128, 4, 2>(ARGS);
     }

@@ -55,13 +55,14 @@ chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restr
     double* X = sm + (size_t)p * ld;                   // [p][ld]: running B (rows > k) / finished X = L^-1 (rows <= k)
     __shared__ int s_bad;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    // sum the split-K partials: partial-major so each thread has p*p/256 independent loads in flight
     for (int e = tid; e < p * p; e += 256) {
         const int i = e % p, j = e / p;
-        double v = 0.0;
-        for (int z = 0; z < splits; z++) v += G[(size_t)z * p * p + e];
-        A[i * ld + j] = v;
+        A[i * ld + j] = G[e];
         X[i * ld + j] = (i == j) ? 1.0 : 0.0;
     }
+    for (int z = 1; z < splits; z++)
+        for (int e = tid; e < p * p; e += 256) A[(e % p) * ld + e / p] += G[(size_t)z * p * p + e];
     if (tid == 0) s_bad = 0;
     __syncthreads();
     double tr = 0.0;
@@ -77,10 +78,24 @@ chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restr
         for (int j = tid; j <= k; j += 256) X[k * ld + j] *= inv;
         __syncthreads();
         // rank-1 updates with column k:  A[i][l] -= L[i][k] L[l][k] (k < l <= i),  B[i][j] -= L[i][k] X[k][j] (j <= k < i)
+        // operands are gathered into registers first so the shared-memory latencies overlap (p <= 112 -> <= 7 per loop)
         for (int i = k + 1 + ty; i < p; i += 16) {
             const double lik = A[i * ld + k];
-            for (int l = k + 1 + tx; l <= i; l += 16) A[i * ld + l] -= lik * A[l * ld + k];
-            for (int j = tx; j <= k; j += 16) X[i * ld + j] -= lik * X[k * ld + j];
+            double av[7], lv[7], xv[7], kv[7];
+#pragma unroll
+            for (int t = 0; t < 7; t++) {
+                const int l = k + 1 + tx + 16 * t;
+                if (l <= i) { av[t] = A[i * ld + l]; lv[t] = A[l * ld + k]; }
+                const int j = tx + 16 * t;
+                if (j <= k) { xv[t] = X[i * ld + j]; kv[t] = X[k * ld + j]; }
+            }
+#pragma unroll
+            for (int t = 0; t < 7; t++) {
+                const int l = k + 1 + tx + 16 * t;
+                if (l <= i) A[i * ld + l] = av[t] - lik * lv[t];
+                const int j = tx + 16 * t;
+                if (j <= k) X[i * ld + j] = xv[t] - lik * kv[t];
+            }
         }
         // no barrier needed before the next pivot read: A[k+1][k+1] is written by its owner above and the
         // barrier at the top of the next iteration orders it (pivot is read before that barrier -> add one)
@@ -98,7 +113,7 @@ chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restr
 // 2x2 block (pair I, pair J), I <= J, of A is transformed once with both rotations (B' = R_I^T B R_J) and
 // mirrored, and V's column pairs are rotated: one pass over A (upper half) and V per round, two barriers.
 // W: column-major eigenvectors, ev: eigenvalues (unsorted).  status[1] = sweeps used.
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* __restrict__ W, double* __restrict__ ev,
                int* __restrict__ status) {
     extern __shared__ double sm[];
@@ -114,12 +129,15 @@ sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* _
     const int tid = threadIdx.x, nthr = blockDim.x;
     for (int e = tid; e < p * p; e += nthr) {
         const int i = e / p, j = e % p;
-        double v = 0.0;
-        if (i < q && j < q)
-            for (int z = 0; z < splits; z++) v += H[(size_t)z * q * q + i + (size_t)q * j] + H[(size_t)z * q * q + j + (size_t)q * i];
-        A[i * ld + j] = 0.5 * v;
+        A[i * ld + j] = 0.0;
         V[i * ld + j] = (i == j) ? 1.0 : 0.0;
     }
+    __syncthreads();
+    for (int z = 0; z < splits; z++)                      // partial-major: independent loads in flight; each (i,j) has
+        for (int e = tid; e < q * q; e += nthr) {         // one owner thread and a fixed summation order (deterministic)
+            const int i = e % q, j = e / q;
+            A[i * ld + j] += 0.5 * (H[(size_t)z * q * q + e] + H[(size_t)z * q * q + j + (size_t)q * i]);
+        }
     __syncthreads();
     double tr = 0.0;
     for (int i = 0; i < p; i++) tr += A[i * ld + i];
@@ -141,20 +159,31 @@ sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* _
                 const double aa = fabs(apq);
                 double c = 1.0, sn = 0.0;
                 if (aa > floor_abs && aa * aa > 1e-30 * fabs(app * aqq)) {
+                    // cos/sin of the double angle, then half-angle: two rsqrt, no division
                     const double zeta = aqq - app, beta = 2.0 * apq;
-                    const double t = (zeta >= 0.0 ? beta : -beta) / (fabs(zeta) + sqrt(zeta * zeta + beta * beta));
-                    c = 1.0 / sqrt(1.0 + t * t);
-                    sn = t * c;
+                    const double inv_r = rsqrt(zeta * zeta + beta * beta);
+                    const double cos2 = fabs(zeta) * inv_r, sin2 = (zeta >= 0.0 ? beta : -beta) * inv_r;
+                    const double c2 = 0.5 + 0.5 * cos2;
+                    const double inv_c = rsqrt(c2);
+                    c = c2 * inv_c;
+                    sn = 0.5 * sin2 * inv_c;
                     any_rot = 1;
                     atomicMax(&s_maxaa, (unsigned long long)__double_as_longlong(aa));
                 }
                 rc[k] = c; rs[k] = sn; rp[k] = pp; rq[k] = qq;
             }
             __syncthreads();
-            // A blocks (I <= J), mirrored
-            for (int e = tid; e < hp * hp; e += nthr) {
-                const int I = e / hp, J = e - I * hp;
-                if (I > J) continue;
+            // A blocks (I <= J), mirrored.  The upper triangle is folded into a (hp/2) x (hp+1) rectangle (rows I and
+            // hp-1-I share a line) so every thread gets a block; odd hp walks the square and skips I > J.
+            const int nblk = (hp & 1) ? hp * hp : (hp / 2) * (hp + 1);
+            for (int e = tid; e < nblk; e += nthr) {
+                int I, J;
+                if (hp & 1) { I = e / hp; J = e - I * hp; if (I > J) continue; }
+                else {
+                    const int I0 = e / (hp + 1), t = e - I0 * (hp + 1);
+                    if (t < hp - I0) { I = I0; J = I0 + t; }
+                    else { I = hp - 1 - I0; J = I + (t - (hp - I0)); }
+                }
                 const int pi = rp[I], qi = rq[I], pj = rp[J], qj = rq[J];
                 const double ci = rc[I], si = rs[I], cj = rc[J], sj = rs[J];
                 const double b11 = A[pi * ld + pj], b12 = A[pi * ld + qj], b21 = A[qi * ld + pj], b22 = A[qi * ld + qj];
@@ -167,14 +196,28 @@ sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* _
                 A[pi * ld + pj] = n11; A[pi * ld + qj] = n12; A[qi * ld + pj] = n21; A[qi * ld + qj] = n22;
                 if (I != J) { A[pj * ld + pi] = n11; A[qj * ld + pi] = n12; A[pj * ld + qi] = n21; A[qj * ld + qi] = n22; }
             }
-            // V column pairs
-            for (int e = tid; e < hp * p; e += nthr) {
-                const int k = e / p, r = e - k * p;
-                const int pp = rp[k], qq = rq[k];
-                const double c = rc[k], sn = rs[k];
-                const double vx = V[r * ld + pp], vy = V[r * ld + qq];
-                V[r * ld + pp] = c * vx - sn * vy;
-                V[r * ld + qq] = sn * vx + c * vy;
+            // V column pairs (4 independent element pairs in flight per thread)
+            for (int e0 = tid; e0 < hp * p; e0 += 4 * nthr) {
+                double vx[4], vy[4], cc[4], ss[4];
+                int ip[4], iq[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int e = e0 + t * nthr;
+                    if (e < hp * p) {
+                        const int k = e / p, r = e - k * p;
+                        ip[t] = r * ld + rp[k]; iq[t] = r * ld + rq[k];
+                        cc[t] = rc[k]; ss[t] = rs[k];
+                        vx[t] = V[ip[t]]; vy[t] = V[iq[t]];
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int e = e0 + t * nthr;
+                    if (e < hp * p) {
+                        V[ip[t]] = cc[t] * vx[t] - ss[t] * vy[t];
+                        V[iq[t]] = ss[t] * vx[t] + cc[t] * vy[t];
+                    }
+                }
             }
             __syncthreads();
         }
@@ -335,7 +378,7 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     const bool dbg = getenv("MPST_SVD_DEBUG") != nullptr;
     if (dbg) cudaStreamSynchronize(c->stream);
     const auto t0 = std::chrono::steady_clock::now();
-    const unsigned eig_threads = p >= 64 ? 512u : 256u;
+    const unsigned eig_threads = p >= 64 ? 1024u : 256u;
 
     auto finish = [&](const char* what, int iters, double res) -> int {
         *chi_new = c->hiscal[0];
