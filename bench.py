@@ -198,6 +198,33 @@ def run_reference(args):
     }))
 
 
+def impute_bench(m, ctx, args):
+    """Second half of BASELINE.json's metric: MPS_impute instances/s (configs[3] shape: T=256, d=16, chi=64,
+    128 contiguous missing sites with a random start, median on the dx=1e-4 grid of 20 001 points) on a bounded
+    batch of instances.  The class MPS is a random chi=64 MPS (imputation cost does not depend on the values)."""
+    T, d, chi, K = 256, 16, 64, 128
+    n = args.impute_instances
+    rng = np.random.default_rng(3)
+    cores = m.generate_starting_mps(chi, T, d, 1, seed=7)
+    ctx.model_init(T, 1, d, chi)
+    ctx.set_cores(cores)
+    t = np.arange(1, T + 1)
+    X = np.sin(2 * np.pi * t[:, None] / 24.0 + rng.uniform(0, 2 * np.pi, n)[None, :]) * 0.45 + 0.04 * rng.standard_normal((T, n))
+    X = np.clip(X, -1, 1)
+    mask = np.zeros((T, n), dtype=np.uint8)
+    for i, s0 in enumerate(rng.integers(0, T - K + 1, n)):
+        mask[s0:s0 + K, i] = 1
+    grid = m.make_grid((-1.0, 1.0), 1e-4)
+    ctx.impute_batch(0, X[:, :64], mask[:, :64], grid)                     # warm-up
+    t0 = time.time()
+    out = ctx.impute_batch(0, X, mask, grid, method="median")
+    dt = time.time() - t0
+    assert np.isfinite(out).all()
+    return {"metric": "MPS_impute instances/sec", "value": n / dt, "unit": "instances/s", "instances": n, "T": T, "d": d,
+            "chi": chi, "missing": K, "grid_points": len(grid), "method": "median", "seconds": dt,
+            "note": "host buffers in/out through mpst_impute_batch (e2e); bounded batch of configs[3]"}
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -208,6 +235,8 @@ def main():
     ap.add_argument("--samples-per-gpu", dest="n", type=int, default=0, help="override samples per GPU (debug)")
     ap.add_argument("--series-length", dest="t", type=int, default=0, help="override series length (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-impute", action="store_true")
+    ap.add_argument("--impute-instances", type=int, default=2048)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -304,6 +333,11 @@ def main():
         "e2e": {"value": e2e, "unit": "sample-bonds/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "roofline": roofline, "device_time_breakdown_ms": breakdown, "wall_s_timed": wall,
     }
+    if not args.no_impute:
+        try:
+            out["impute"] = impute_bench(m, ctx, args)
+        except Exception as e:
+            out["impute"] = {"value": None, "error": repr(e)}
     if not args.no_cpu_baseline:
         try:
             n_sample, n_bonds = 1024, 24

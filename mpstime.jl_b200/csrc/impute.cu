@@ -17,6 +17,7 @@
 // is projected in (v <- state . A) and the walk continues.  Results are scale invariant, so v
 // and G are renormalised freely to stay in range.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include "mpst_common.cuh"
 #include "encode_device.cuh"
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                         }
                         __syncthreads();
                         gsel = s_misc[3];
+                        if (gsel < 0 || gsel >= G) gsel = 0;          // non-finite pdf (NaN in the cores): stay in bounds
                         xsel = P.grid[gsel];
                     } else if (P.method == MPST_IMPUTE_MODE) {
                         double best = -1.0; int bg = 0x7fffffff;

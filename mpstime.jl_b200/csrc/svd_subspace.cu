@@ -3,8 +3,8 @@
 // Only the chi_max largest singular triplets of M (m x n) survive decomposeBT's truncation
 // (reference Training/RealRealHighDimension.jl:146-203) and the NDTensors rule needs nothing of the rest but
 // its total weight ||M||_F^2 - sum(kept sigma^2).  The singular values of a trained bond tensor decay
-// geometrically (measured: sigma_{2k+16}/sigma_k ~ 1e-2 at k = 40), so a subspace of p = 2k+16 vectors
-// converges at (sigma_{p+1}/sigma_k)^2 per iteration: 3-4 iterations reach rounding level where the full
+// geometrically (measured: sigma_{2k}/sigma_k ~ 1e-1..1e-2 at k = 40), so a subspace of p = 2k vectors
+// converges at (sigma_{p+1}/sigma_k)^2 per iteration: 5 iterations reach rounding level where the full
 // one-sided Jacobi needs 20-30 latency-bound sweeps.
 //   Q <- orth(random n x p)
 //   repeat:  Z <- orth(M Q);  Q <- orth(M^T Z)              (orth = Cholesky-QR, twice on the last pass)
@@ -351,7 +351,9 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     else if (m <= PMAX && m < n) { mode = 1; p = m + (m & 1); }
     else {
         mode = 2;
-        p = std::min((int)round_up(2 * k + 16, 16), PMAX);
+        // measured on trained bonds (k = 40): p = 80 with 5 iterations beats p = 96 with 4 and p = 112 with 3 --
+        // the p^3 single-CTA kernels (Cholesky, Rayleigh-Ritz eigen-solver) dominate, not the GEMMs
+        p = std::min((int)round_up(2 * k + (getenv("MPST_SVD_OVS") ? atoi(getenv("MPST_SVD_OVS")) : 0), 16), PMAX);
         if (p < k + 32 || n <= p || m < p) return MPST_OK;            // too little oversampling: full Jacobi
     }
     const size_t need = (size_t)2 * n * p + (size_t)2 * m * p + (size_t)(MAXSPLIT + 3) * p * p + (size_t)n * k +
@@ -452,7 +454,7 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     const int max_rounds = 3;
     int iters_done = 0;
     for (int round = 0; round < max_rounds; round++) {
-        const int niter = round == 0 ? (p >= 2 * k ? 4 : 6) : 3;
+        const int niter = round == 0 ? (getenv("MPST_SVD_IT") ? atoi(getenv("MPST_SVD_IT")) : (p >= 2 * k ? 5 : 7)) : 3;
         for (int it = 0; it < niter; it++) {
             TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, Qa, n, Za, m));            // Z = M Q
             TRY(cholqr(Za, Zb, m));

@@ -126,6 +126,7 @@ def generate_starting_mps(chi_init, T, d, C, seed=1234):
         a, s, b = cores[j].shape
         Q, R = np.linalg.qr(cores[j].reshape(a * s, b))
         cores[j] = Q.reshape(a, s, Q.shape[1])
-        cores[j + 1] = np.tensordot(R, cores[j + 1], axes=(1, 0))
+        nxt = np.tensordot(R, cores[j + 1], axes=(1, 0))
+        cores[j + 1] = nxt / np.linalg.norm(nxt)             # keep the running scale at 1 (long chains overflow otherwise)
     cores[-1] = cores[-1] / np.linalg.norm(cores[-1])
     return cores

@@ -292,8 +292,8 @@ def random_start_mps(T, d, chi_init, C, seed=1234):
         Q, R = np.linalg.qr(A.reshape(a * s, b))
         k = Q.shape[1]
         cores[j] = Q.reshape(a, s, k)
-        nxt = cores[j + 1]
-        cores[j + 1] = np.tensordot(R, nxt, axes=(1, 0))
+        nxt = np.tensordot(R, cores[j + 1], axes=(1, 0))
+        cores[j + 1] = nxt / np.linalg.norm(nxt)             # keep the running scale at 1 (long chains overflow otherwise)
     n2 = _norm2_general(cores)
     cores[-1] = cores[-1] / np.sqrt(n2)
     return cores
