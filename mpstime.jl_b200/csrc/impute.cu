@@ -18,8 +18,10 @@
 // and G are renormalised freely to stay in range.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "mpst_common.cuh"
+#include "dmma.cuh"
 #include "encode_device.cuh"
 
 namespace {
@@ -37,7 +39,7 @@ struct ImpParams {
     double* out;                // [n][ntraj][T]
     double* gr_scratch;         // [grid][Kmax][chimax^2]
     double* p_scratch;          // [grid][G]
-    int T, d, G, ntraj, Kmax, chimax, method, basis;
+    int T, d, G, ntraj, Kmax, chimax, method, basis, debug;
     int64_t n;
     double max_jump;
 };
@@ -48,40 +50,45 @@ __device__ __forceinline__ void encode_any(int basis, double x, int d, double* v
     else encode_point<MPST_BASIS_UNIFORM>(x, d, v);
 }
 
-// C[n x n2] = A[n x k] * B[k x n2] (or B^T when TB), all in shared memory with pitch ld.
+// C[n8 x n8] (+)= A * B  (or A * B^T when TB) on the FP64 tensor cores; all operands in shared memory with pitch
+// ld == 4 (mod 16) doubles (conflict-free DMMA fragment loads), dimensions padded with zeros to a multiple of 8.
+// 8 warps; each warp owns 8x8 output blocks in a strided fashion.
 template <bool TB, bool ACC>
-__device__ __forceinline__ void smem_matmul(double* __restrict__ Cm, const double* __restrict__ A,
-                                            const double* __restrict__ B, int n, int k, int n2, int ld) {
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    for (int i0 = 0; i0 < n; i0 += 64)
-        for (int j0 = 0; j0 < n2; j0 += 64) {
-            double acc[4][4];
+__device__ __forceinline__ void smem_dmma_matmul(double* __restrict__ Cm, const double* __restrict__ A,
+                                                 const double* __restrict__ B, int n8, int ld) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fc = lane & 3;
+    const int nb = n8 >> 3;
+    // each warp: block rows i = warp, warp+8, ... ; all block columns, two at a time
+    for (int bi = warp; bi < nb; bi += 8) {
+        for (int bj = 0; bj < nb; bj += 8) {
+            double c[8][2];
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+            for (int t = 0; t < 8; t++) {
+                const int j = (bj + t) * 8 + 2 * fc;
+                if (ACC && bj + t < nb) { c[t][0] = Cm[(bi * 8 + fr) * ld + j]; c[t][1] = Cm[(bi * 8 + fr) * ld + j + 1]; }
+                else { c[t][0] = 0.0; c[t][1] = 0.0; }
+            }
+            for (int k0 = 0; k0 < n8; k0 += 4) {
+                const double av = A[(bi * 8 + fr) * ld + k0 + fc];
 #pragma unroll
-                for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-            for (int kk = 0; kk < k; kk++) {
-                double av[4], bv[4];
-#pragma unroll
-                for (int a = 0; a < 4; a++) { const int i = i0 + ty + 16 * a; av[a] = i < n ? A[i * ld + kk] : 0.0; }
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int j = j0 + tx + 16 * b;
-                    bv[b] = j < n2 ? (TB ? B[j * ld + kk] : B[kk * ld + j]) : 0.0;
+                for (int t = 0; t < 8; t++) {
+                    if (bj + t < nb) {
+                        const int jb = (bj + t) * 8;
+                        const double bv = TB ? B[(jb + fr) * ld + k0 + fc] : B[(k0 + fc) * ld + jb + fr];
+                        dmma_8x8x4(c[t][0], c[t][1], av, bv);
+                    }
                 }
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int b = 0; b < 4; b++) acc[a][b] += av[a] * bv[b];
             }
 #pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
-                    if (i < n && j < n2) { if (ACC) Cm[i * ld + j] += acc[a][b]; else Cm[i * ld + j] = acc[a][b]; }
+            for (int t = 0; t < 8; t++)
+                if (bj + t < nb) {
+                    const int j = (bj + t) * 8 + 2 * fc;
+                    Cm[(bi * 8 + fr) * ld + j] = c[t][0];
+                    Cm[(bi * 8 + fr) * ld + j + 1] = c[t][1];
                 }
         }
+    }
 }
 
 __device__ __forceinline__ double block_reduce_sum(double v, double* sh) {
@@ -105,33 +112,180 @@ __device__ __forceinline__ double block_reduce_max(double v, double* sh) {
     return t;
 }
 
+// Bonnet recurrence P_l = a_l x P_{l-1} - b_l P_{l-2},  a_l = (2l-1)/l,  b_l = (l-1)/l
+__constant__ double c_leg_a[MPST_MAX_D];
+__constant__ double c_leg_b[MPST_MAX_D];
+
+// p[g] = || rho Phi(x_g) ||^2 for the Legendre bases, NP grid points per thread at a time.  R[s][l] = rho[s][l] *
+// sqrt((2l+1)/2) (zero padded to D x D) sits in shared memory (broadcast reads); P_l(x) comes from the Bonnet
+// recurrence with compile-time coefficients, accumulators stay in registers.
+template <int D, int NP>
+__device__ __forceinline__ void pdf_legendre(const double* __restrict__ Rt, const double* __restrict__ grid, int g0, int g1,
+                                             double* __restrict__ pbuf) {
+    // Rt[l][s] (s contiguous, 16-byte aligned rows): one LDS.128 feeds 2*NP DFMAs
+    for (int g = g0; g < g1; g += NP) {
+        double x[NP], pm[NP], pc[NP], t[NP][D];
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            x[q] = grid[min(g + q, g1 - 1)];
+            pm[q] = 1.0; pc[q] = 1.0;
+#pragma unroll
+            for (int s = 0; s < D; s++) t[q][s] = 0.0;
+        }
+#pragma unroll 1
+        for (int l = 0; l < D; l++) {
+            if (l == 1) {
+#pragma unroll
+                for (int q = 0; q < NP; q++) pc[q] = x[q];
+            } else if (l > 1) {
+                const double al = c_leg_a[l], bl = c_leg_b[l];
+#pragma unroll
+                for (int q = 0; q < NP; q++) { const double pn = al * x[q] * pc[q] - bl * pm[q]; pm[q] = pc[q]; pc[q] = pn; }
+            }
+#pragma unroll
+            for (int s = 0; s < D; s += 2) {
+                const double2 r = *reinterpret_cast<const double2*>(Rt + l * D + s);
+#pragma unroll
+                for (int q = 0; q < NP; q++) { t[q][s] += r.x * pc[q]; t[q][s + 1] += r.y * pc[q]; }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            if (g + q < g1) {
+                double pv = 0.0;
+#pragma unroll
+                for (int s = 0; s < D; s++) pv += t[q][s] * t[q][s];
+                pbuf[g + q] = pv;
+            }
+        }
+    }
+}
+
+// exclusive prefix sum of one value per thread over the block (warp shuffles + one smem hop); total in `total`
+__device__ __forceinline__ double block_excl_scan(double v, double* scr, double& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) scr[warp] = inc;
+    __syncthreads();
+    double off = 0.0, tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; w++) {
+        const double t = scr[w];
+        if (w < warp) off += t;
+        tot += t;
+    }
+    total = tot;
+    return off + inc - v;
+}
+
+// block-wide lexicographic best of (value, index): smallest (MAXI = false) or largest (MAXI = true) value, ties to the
+// smaller index.  Every thread gets the winning index.
+template <bool MAXI>
+__device__ __forceinline__ int block_argbest(double v, int i, double* scr) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, v, o);
+        const int oi = __shfl_down_sync(0xffffffffu, i, o);
+        const bool better = MAXI ? (ov > v) : (ov < v);
+        if (better || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+    int* si = reinterpret_cast<int*>(scr + NT / 32);
+    __syncthreads();
+    if (lane == 0) { scr[warp] = v; si[warp] = i; }
+    __syncthreads();
+    v = scr[0]; i = si[0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; w++) {
+        const double ov = scr[w];
+        const int oi = si[w];
+        const bool better = MAXI ? (ov > v) : (ov < v);
+        if (better || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+    return i;
+}
+
+// stage slice s of a core ([s][a][b], cl x cr) into the zero-padded n8 x n8 shared tile
+__device__ __forceinline__ void stage_slice(double* __restrict__ As, const double* __restrict__ A, int s, int cl, int cr,
+                                            int n8, int ld) {
+    const double* src = A + (size_t)s * cl * cr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int a = warp; a < n8; a += NT / 32)
+        for (int b = lane; b < n8; b += 32) As[a * ld + b] = (a < cl && b < cr) ? src[a * cr + b] : 0.0;
+}
+
 __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
     extern __shared__ double sm[];
-    const int ld = P.chimax + 1;                       // odd-ish pitch against bank conflicts
-    const int msz = P.chimax * ld;
+    const int n8 = (P.chimax + 7) & ~7;
+    const int ld = n8 + 4;                             // == 4 (mod 16) when n8 is a multiple of 16; see launch check
+    const int msz = n8 * ld;
     double* Gm = sm;                                   // current right Gram
-    double* Gn = Gm + msz;                             // next
+    double* Gn = Gm + msz;                             // next / accumulator
     double* As = Gn + msz;                             // staged A_s / M
     double* T1 = As + msz;                             // temp product
-    double* vec = T1 + msz;                            // [chimax] left vector / right vector
-    double* vec2 = vec + P.chimax;
-    double* Ad = vec2 + P.chimax;                      // [d][ld]
+    double* vec = T1 + msz;                            // [n8] left / right vector
+    double* vec2 = vec + n8;
+    double* Ad = vec2 + n8;                            // [d][ld]
     double* Td = Ad + P.d * ld;                        // [d][ld]
     double* rho = Td + P.d * ld;                       // [d][d]
     double* rho2 = rho + P.d * P.d;                    // [d][d]
     double* phi = rho2 + P.d * P.d;                    // [d]
     double* red = phi + MPST_MAX_D;                    // [32] reductions
-    double* scr = red + 32;                            // [3*NT + 16] scan / arg-reduction scratch
+    double* scr = red + 32;                            // [max(3*NT + 16, 4*n8)] scan / partial-sum scratch
+    double* pdfR = scr + max(3 * NT + 16, 4 * n8);     // [32*32] rho * normalisation for the Legendre pdf
     __shared__ int s_misc[4];
     const int tid = threadIdx.x;
     const int T = P.T, d = P.d, G = P.G;
+    const int grp = tid >> 6, l64 = tid & 63;          // 4 groups of 64 threads for the vector contractions
     double* GR = P.gr_scratch + (size_t)blockIdx.x * P.Kmax * P.chimax * P.chimax;
     double* pbuf = P.p_scratch + (size_t)blockIdx.x * G;
 
+    // out[i] = sum_j As[i][j] * v[j]  (ROWS) or out[j] = sum_i v[i] As[i][j] (COLS), accumulated with weight wgt
+    // into acc[] (per-thread partials over its quarter of the contracted index); finished by reduce_partials.
+    auto contract_rows = [&](double wgt, int cl, int cr, double* acc) {      // index i = l64 (+64), group splits j
+        const int j0 = grp * ((cr + 3) / 4), j1 = min(cr, j0 + (cr + 3) / 4);
+        for (int q = 0, i = l64; i < cl; i += 64, q++) {
+            double t = 0.0;
+            for (int j = j0; j < j1; j++) t += As[i * ld + j] * vec[j];
+            acc[q] += wgt * t;
+        }
+    };
+    auto contract_cols = [&](double wgt, int cl, int cr, double* acc) {      // index j = l64 (+64), group splits i
+        const int i0 = grp * ((cl + 3) / 4), i1 = min(cl, i0 + (cl + 3) / 4);
+        for (int q = 0, j = l64; j < cr; j += 64, q++) {
+            double t = 0.0;
+            for (int i = i0; i < i1; i++) t += vec[i] * As[i * ld + j];
+            acc[q] += wgt * t;
+        }
+    };
+    auto reduce_partials = [&](const double* acc, int n, double* out) {     // out[i] = sum over the 4 groups
+        for (int q = 0, i = l64; i < n8; i += 64, q++) scr[grp * n8 + i] = (i < n) ? acc[q] : 0.0;
+        __syncthreads();
+        for (int i = tid; i < n8; i += NT) out[i] = scr[i] + scr[n8 + i] + scr[2 * n8 + i] + scr[3 * n8 + i];
+        __syncthreads();
+    };
+    auto normalise_into_vec = [&](int n) {                                   // vec <- vec2 / ||vec2||
+        double nn = 0.0;
+        for (int i = tid; i < n; i += NT) nn += vec2[i] * vec2[i];
+        nn = block_reduce_sum(nn, red);
+        const double sc = nn > 0.0 ? rsqrt(nn) : 1.0;
+        for (int i = tid; i < n8; i += NT) vec[i] = i < n ? vec2[i] * sc : 0.0;
+        __syncthreads();
+    };
+
+    long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tq = 0;
+#define TICK() do { if (P.debug) tq = clock64(); } while (0)
+#define TOCK(i) do { if (P.debug) tm[i] += clock64() - tq; } while (0)
     for (int64_t inst = blockIdx.x; inst < P.n; inst += gridDim.x) {
         const double* x = P.X + inst * T;
         const uint8_t* mk = P.mask + inst * T;
-        // first / last missing site and count
         if (tid == 0) {
             int first = -1, last = -1, K = 0;
             for (int j = 0; j < T; j++) if (mk[j]) { if (first < 0) first = j; last = j; K++; }
@@ -145,34 +299,32 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
 
         // ---------------- backward pass: right Gram matrices ------------------------------------
         // right of the last missing site everything is known: rank-1 Gram r r^T, carry the vector r
-        for (int b = tid; b < P.chimax; b += NT) vec[b] = (b == 0) ? 1.0 : 0.0;
+        for (int b = tid; b < n8; b += NT) vec[b] = (b == 0) ? 1.0 : 0.0;
         __syncthreads();
+        TICK();
         for (int j = T - 1; j > last; j--) {
             const int cl = P.chi[j], cr = P.chi[j + 1];
             if (tid == 0) encode_any(P.basis, x[j], d, phi);
-            __syncthreads();
             const double* A = P.cores + P.core_off[j];           // [s][a][b]
-            for (int a = tid; a < cl; a += NT) {
-                double acc = 0.0;
-                for (int s = 0; s < d; s++) {
-                    const double* row = A + ((size_t)s * cl + a) * cr;
-                    double t = 0.0;
-                    for (int b = 0; b < cr; b++) t += row[b] * vec[b];
-                    acc += phi[s] * t;
-                }
-                vec2[a] = acc;
+            double acc[2] = {0.0, 0.0};
+            for (int s = 0; s < d; s++) {
+                __syncthreads();
+                stage_slice(As, A, s, cl, cr, n8, ld);
+                __syncthreads();
+                contract_rows(phi[s], cl, cr, acc);               // r'[a] += phi_s sum_b A_s[a][b] r[b]
             }
             __syncthreads();
-            double nn = 0.0;
-            for (int a = tid; a < cl; a += NT) nn += vec2[a] * vec2[a];
-            nn = block_reduce_sum(nn, red);
-            const double sc = nn > 0.0 ? rsqrt(nn) : 1.0;
-            for (int a = tid; a < P.chimax; a += NT) vec[a] = a < cl ? vec2[a] * sc : 0.0;
-            __syncthreads();
+            reduce_partials(acc, cl, vec2);
+            normalise_into_vec(cl);
         }
-        {   // G = r r^T  (dimension chi[last+1])
+        TOCK(0);
+        TICK();
+        {   // G = r r^T  (dimension chi[last+1]), zero padded
             const int cr = P.chi[last + 1];
-            for (int e = tid; e < cr * cr; e += NT) Gm[(e / cr) * ld + (e % cr)] = vec[e / cr] * vec[e % cr];
+            for (int e = tid; e < n8 * n8; e += NT) {
+                const int a = e / n8, b = e - a * n8;
+                Gm[a * ld + b] = (a < cr && b < cr) ? vec[a] * vec[b] : 0.0;
+            }
             __syncthreads();
         }
         int kidx = K - 1;
@@ -180,48 +332,52 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
             const int cl = P.chi[j], cr = P.chi[j + 1];
             const double* A = P.cores + P.core_off[j];
             if (mk[j]) {
-                // store the Gram this missing site sees
-                double* dst = GR + (size_t)kidx * P.chimax * P.chimax;
+                double* dst = GR + (size_t)kidx * P.chimax * P.chimax;     // the Gram this missing site sees
                 for (int e = tid; e < cr * cr; e += NT) dst[e] = Gm[(e / cr) * ld + (e % cr)];
                 kidx--;
                 if (j == first) break;
-                for (int e = tid; e < cl * cl; e += NT) Gn[(e / cl) * ld + (e % cl)] = 0.0;
+                for (int e = tid; e < n8 * n8; e += NT) Gn[(e / n8) * ld + (e % n8)] = 0.0;
                 for (int s = 0; s < d; s++) {
                     __syncthreads();
-                    for (int e = tid; e < cl * cr; e += NT) As[(e / cr) * ld + (e % cr)] = A[(size_t)s * cl * cr + e];
+                    stage_slice(As, A, s, cl, cr, n8, ld);
                     __syncthreads();
-                    smem_matmul<false, false>(T1, As, Gm, cl, cr, cr, ld);      // T1 = A_s G
+                    smem_dmma_matmul<false, false>(T1, As, Gm, n8, ld);        // T1 = A_s G
                     __syncthreads();
-                    smem_matmul<true, true>(Gn, T1, As, cl, cr, cl, ld);        // Gn += T1 A_s^T
+                    smem_dmma_matmul<true, true>(Gn, T1, As, n8, ld);          // Gn += T1 A_s^T
                 }
             } else {
                 if (tid == 0) encode_any(P.basis, x[j], d, phi);
-                __syncthreads();
-                for (int e = tid; e < cl * cr; e += NT) {
-                    double acc = 0.0;
-                    for (int s = 0; s < d; s++) acc += phi[s] * A[(size_t)s * cl * cr + e];
-                    As[(e / cr) * ld + (e % cr)] = acc;                         // M
+                for (int e = tid; e < n8 * n8; e += NT) Gn[(e / n8) * ld + (e % n8)] = 0.0;   // M accumulates in Gn
+                for (int s = 0; s < d; s++) {
+                    __syncthreads();
+                    stage_slice(As, A, s, cl, cr, n8, ld);
+                    __syncthreads();
+                    const double ps = phi[s];
+                    for (int e = tid; e < n8 * n8; e += NT) { const int o = (e / n8) * ld + (e % n8); Gn[o] += ps * As[o]; }
                 }
                 __syncthreads();
-                smem_matmul<false, false>(T1, As, Gm, cl, cr, cr, ld);          // T1 = M G
+                for (int e = tid; e < n8 * n8; e += NT) { const int o = (e / n8) * ld + (e % n8); As[o] = Gn[o]; }
                 __syncthreads();
-                smem_matmul<true, false>(Gn, T1, As, cl, cr, cl, ld);           // Gn = T1 M^T
+                smem_dmma_matmul<false, false>(T1, As, Gm, n8, ld);            // T1 = M G
+                __syncthreads();
+                smem_dmma_matmul<true, false>(Gn, T1, As, n8, ld);             // Gn = T1 M^T
             }
             __syncthreads();
             // renormalise (scale invariance) and swap
             double mx = 0.0;
-            for (int e = tid; e < cl * cl; e += NT) mx = fmax(mx, fabs(Gn[(e / cl) * ld + (e % cl)]));
+            for (int e = tid; e < n8 * n8; e += NT) mx = fmax(mx, fabs(Gn[(e / n8) * ld + (e % n8)]));
             mx = block_reduce_max(mx, red);
             const double sc = mx > 0.0 ? 1.0 / mx : 1.0;
-            for (int e = tid; e < cl * cl; e += NT) Gm[(e / cl) * ld + (e % cl)] = Gn[(e / cl) * ld + (e % cl)] * sc;
+            for (int e = tid; e < n8 * n8; e += NT) { const int o = (e / n8) * ld + (e % n8); Gm[o] = Gn[o] * sc; }
             __syncthreads();
         }
         __syncthreads();
+        TOCK(1);
 
         // ---------------- forward pass(es) ---------------------------------------------------------
         for (int tr = 0; tr < P.ntraj; tr++) {
             double* xo = P.out + (inst * P.ntraj + tr) * T;
-            for (int a = tid; a < P.chimax; a += NT) vec[a] = (a == 0) ? 1.0 : 0.0;
+            for (int a = tid; a < n8; a += NT) vec[a] = (a == 0) ? 1.0 : 0.0;
             __syncthreads();
             int k = 0;
             double x_prev = 0.0;
@@ -229,28 +385,33 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
             for (int j = 0; j <= last; j++) {
                 const int cl = P.chi[j], cr = P.chi[j + 1];
                 const double* A = P.cores + P.core_off[j];
+                TICK();
                 if (!mk[j]) {
                     if (tid == 0) encode_any(P.basis, x[j], d, phi);
-                    __syncthreads();
-                    for (int b = tid; b < cr; b += NT) {
-                        double acc = 0.0;
-                        for (int s = 0; s < d; s++) {
-                            double t = 0.0;
-                            for (int a = 0; a < cl; a++) t += vec[a] * A[((size_t)s * cl + a) * cr + b];
-                            acc += phi[s] * t;
-                        }
-                        vec2[b] = acc;
+                    double acc[2] = {0.0, 0.0};
+                    for (int s = 0; s < d; s++) {
+                        __syncthreads();
+                        stage_slice(As, A, s, cl, cr, n8, ld);
+                        __syncthreads();
+                        contract_cols(phi[s], cl, cr, acc);           // v'[b] += phi_s sum_a v[a] A_s[a][b]
                     }
+                    __syncthreads();
+                    reduce_partials(acc, cr, vec2);
                     x_prev = x[j];
                     have_prev = true;
+                    TOCK(2);
                 } else {
                     // A_d[s][b] = sum_a v[a] A[s][a][b]
-                    for (int e = tid; e < d * cr; e += NT) {
-                        const int s = e / cr, b = e % cr;
-                        double t = 0.0;
-                        for (int a = 0; a < cl; a++) t += vec[a] * A[((size_t)s * cl + a) * cr + b];
-                        Ad[s * ld + b] = t;
+                    for (int s = 0; s < d; s++) {
+                        __syncthreads();
+                        stage_slice(As, A, s, cl, cr, n8, ld);
+                        __syncthreads();
+                        double acc[2] = {0.0, 0.0};
+                        contract_cols(1.0, cl, cr, acc);
+                        reduce_partials(acc, cr, Ad + s * ld);
                     }
+                    TOCK(3);
+                    TICK();
                     const double* Gk = GR + (size_t)k * P.chimax * P.chimax;
                     for (int e = tid; e < cr * cr; e += NT) Gm[(e / cr) * ld + (e % cr)] = Gk[e];
                     __syncthreads();
@@ -281,63 +442,62 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                     __syncthreads();
                     for (int e = tid; e < d * d; e += NT) rho[e] = rho2[e];
                     __syncthreads();
+                    TOCK(4);
+                    TICK();
                     // pdf on the grid: p[g] = || rho Phi_g ||^2   (thread-contiguous chunks for the scan)
                     const int per = (G + NT - 1) / NT;
                     const int g0 = tid * per, g1 = min(G, g0 + per);
-                    for (int g = g0; g < g1; g++) {
-                        const double* ph = P.genc + (size_t)g * d;
-                        double pv = 0.0;
-                        for (int s = 0; s < d; s++) {
-                            double t = 0.0;
-                            for (int t2 = 0; t2 < d; t2++) t += rho[s * d + t2] * ph[t2];
-                            pv += t * t;
+                    if (P.basis == MPST_BASIS_LEGENDRE_NO_NORM || P.basis == MPST_BASIS_LEGENDRE_NORM) {
+                        // R = rho * diag(sqrt((2l+1)/2)), zero padded to the next supported order (in scr/rho2 space)
+                        const int D = d <= 8 ? 8 : d <= 16 ? 16 : d <= 24 ? 24 : 32;
+                        double* Rm = pdfR;
+                        for (int e = tid; e < D * D; e += NT) {
+                            const int l = e / D, s = e - l * D;
+                            Rm[e] = (s < d && l < d) ? rho[s * d + l] * sqrt((double)(2 * l + 1) * 0.5) : 0.0;
                         }
-                        pbuf[g] = pv;
+                        __syncthreads();
+                        if (D == 8) pdf_legendre<8, 4>(Rm, P.grid, g0, g1, pbuf);
+                        else if (D == 16) pdf_legendre<16, 2>(Rm, P.grid, g0, g1, pbuf);
+                        else if (D == 24) pdf_legendre<24, 2>(Rm, P.grid, g0, g1, pbuf);
+                        else pdf_legendre<32, 2>(Rm, P.grid, g0, g1, pbuf);
+                    } else {
+                        for (int g = g0; g < g1; g++) {
+                            double ph[MPST_MAX_D];
+                            encode_any(P.basis, P.grid[g], d, ph);
+                            double pv = 0.0;
+                            for (int s = 0; s < d; s++) {
+                                double t = 0.0;
+                                for (int t2 = 0; t2 < d; t2++) t += rho[s * d + t2] * ph[t2];
+                                pv += t * t;
+                            }
+                            pbuf[g] = pv;
+                        }
                     }
                     __syncthreads();
+                    TOCK(5);
+                    TICK();
                     int gsel = 0;
                     double xsel = 0.0;
                     if (P.method == MPST_IMPUTE_MEDIAN || P.method == MPST_IMPUTE_ITS) {
                         // cumulative trapezoid c[g] = c[g-1] + (p[g-1] + p[g]), scaled by h = (x1-x0)/2
                         double loc = 0.0;
                         for (int g = max(g0, 1); g < g1; g++) loc += pbuf[g - 1] + pbuf[g];
-                        // exclusive prefix over threads (NT partial sums, serial in thread 0: NT is small)
-                        double* pre = scr;                                   // NT+1 doubles
-                        pre[tid] = loc;
-                        __syncthreads();
-                        if (tid == 0) {
-                            double run = 0.0;
-                            for (int t2 = 0; t2 < NT; t2++) { const double v = pre[t2]; pre[t2] = run; run += v; }
-                            pre[NT] = run;
-                        }
-                        __syncthreads();
+                        double tot;
+                        const double pre_t = block_excl_scan(loc, scr, tot);
                         const double h = (P.grid[1] - P.grid[0]) * 0.5;
-                        const double Z = h * pre[NT];
+                        const double Z = h * tot;
                         const double u = (P.method == MPST_IMPUTE_MEDIAN) ? 0.5
                                          : P.uniforms[((size_t)inst * P.ntraj + tr) * P.Kmax + k];
                         double best = 1e300;
                         int bg = 0x7fffffff;
-                        double run = pre[tid];
+                        double run = pre_t;
                         for (int g = g0; g < g1; g++) {
                             if (g > 0) run += pbuf[g - 1] + pbuf[g];
                             const double cg = h * run;
                             const double val = fabs(cg / Z - u);
                             if (val < best) { best = val; bg = g; }
                         }
-                        // lexicographic (val, g) minimum over the block
-                        double* bv = scr;
-                        int* bi = reinterpret_cast<int*>(scr + NT + 2);
-                        __syncthreads();
-                        bv[tid] = best; bi[tid] = bg;
-                        __syncthreads();
-                        if (tid == 0) {
-                            double b0 = bv[0]; int i0 = bi[0];
-                            for (int t2 = 1; t2 < NT; t2++)
-                                if (bv[t2] < b0 || (bv[t2] == b0 && bi[t2] < i0)) { b0 = bv[t2]; i0 = bi[t2]; }
-                            s_misc[3] = i0;
-                        }
-                        __syncthreads();
-                        gsel = s_misc[3];
+                        gsel = block_argbest<false>(best, bg, scr);
                         if (gsel < 0 || gsel >= G) gsel = 0;          // non-finite pdf (NaN in the cores): stay in bounds
                         xsel = P.grid[gsel];
                     } else if (P.method == MPST_IMPUTE_MODE) {
@@ -349,20 +509,9 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                             if (pv > bestall) { bestall = pv; bgall = g; }
                             if (!filt || fabs(P.grid[g] - x_prev) <= P.max_jump) if (pv > best) { best = pv; bg = g; }
                         }
-                        double* bv = scr; int* bi = reinterpret_cast<int*>(scr + 2 * NT + 2);
-                        __syncthreads();
-                        bv[tid] = best; bi[tid] = bg; bv[NT + tid] = bestall; bi[NT + tid] = bgall;
-                        __syncthreads();
-                        if (tid == 0) {
-                            double b0 = -1.0; int i0 = 0x7fffffff; double b1 = -1.0; int i1 = 0x7fffffff;
-                            for (int t2 = 0; t2 < NT; t2++) {
-                                if (bv[t2] > b0 || (bv[t2] == b0 && bi[t2] < i0)) { b0 = bv[t2]; i0 = bi[t2]; }
-                                if (bv[NT + t2] > b1 || (bv[NT + t2] == b1 && bi[NT + t2] < i1)) { b1 = bv[NT + t2]; i1 = bi[NT + t2]; }
-                            }
-                            s_misc[3] = (i0 != 0x7fffffff) ? i0 : i1;      // no admissible point: global argmax (:137-141)
-                        }
-                        __syncthreads();
-                        gsel = s_misc[3];
+                        const int i0 = block_argbest<true>(best, bg, scr);
+                        const int i1 = block_argbest<true>(bestall, bgall, scr);
+                        gsel = (i0 != 0x7fffffff) ? i0 : i1;               // no admissible point: global argmax (:137-141)
                         xsel = P.grid[gsel];
                     } else {   // mean (sampling_utils.jl:64-101): E[x] = sum x p dx / Z, Z = trapz
                         double sp = 0.0, sxp = 0.0;
@@ -378,6 +527,7 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                         xsel = sxp * dx / Z;
                         gsel = -1;
                     }
+                    TOCK(6);
                     if (tid == 0) xo[j] = xsel;
                     // state of the chosen value, then v <- state . A_d
                     if (gsel >= 0) { for (int s = tid; s < d; s += NT) phi[s] = P.genc[(size_t)gsel * d + s]; }
@@ -397,12 +547,17 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                 for (int b = tid; b < cr; b += NT) nn += vec2[b] * vec2[b];
                 nn = block_reduce_sum(nn, red);
                 const double sc = nn > 0.0 ? rsqrt(nn) : 1.0;
-                for (int b = tid; b < P.chimax; b += NT) vec[b] = b < cr ? vec2[b] * sc : 0.0;
+                for (int b = tid; b < n8; b += NT) vec[b] = b < cr ? vec2[b] * sc : 0.0;
                 __syncthreads();
             }
         }
         __syncthreads();
     }
+    if (P.debug && blockIdx.x == 0 && tid == 0)
+        printf("[impute cycles] bwd-vector %lld  bwd-gram %lld  fwd-known %lld  fwd-Ad %lld  rho %lld  pdf %lld  select %lld\n", tm[0], tm[1],
+               tm[2], tm[3], tm[4], tm[5], tm[6]);
+#undef TICK
+#undef TOCK
 }
 
 // class slice of one core -> [s][a][b]
@@ -444,10 +599,10 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
         off[j] = tot;
         tot += (int64_t)d * k.chi_l * k.chi_r;
     }
-    const int ld = chimax + 1;
-    const size_t smem = sizeof(double) * ((size_t)4 * chimax * ld + 2 * chimax + 2 * (size_t)d * ld + 2 * (size_t)d * d + MPST_MAX_D + 32 +
-                                          3 * NT + 16);
-    if (smem > 227 * 1024) { c->err = "impute_batch: chi too large for the shared-memory Gram matrices (chi <= 76 at d = 16)"; return MPST_E_UNSUPPORTED; }
+    const int n8 = (chimax + 7) & ~7, ld = n8 + 4;
+    const size_t smem = sizeof(double) * ((size_t)4 * n8 * ld + 2 * n8 + 2 * (size_t)d * ld + 2 * (size_t)d * d + MPST_MAX_D + 32 +
+                                          std::max(3 * NT + 16, 4 * n8) + MPST_MAX_D * MPST_MAX_D);
+    if (smem > 227 * 1024) { c->err = "impute_batch: chi too large for the shared-memory Gram matrices (chi <= 72 at d = 16)"; return MPST_E_UNSUPPORTED; }
     // host-side Kmax
     int Kmax = 0;
     for (int64_t i = 0; i < n; i++) { int k = 0; for (int j = 0; j < T; j++) k += missing[i * T + j] ? 1 : 0; Kmax = std::max(Kmax, k); }
@@ -499,6 +654,15 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     P.uniforms = dunif; P.out = dout; P.gr_scratch = dGR; P.p_scratch = dp;
     P.T = T; P.d = d; P.G = G; P.ntraj = n_traj; P.Kmax = Kmax; P.chimax = chimax; P.method = method; P.basis = c->basis;
     P.n = n; P.max_jump = max_jump;
+    P.debug = getenv("MPST_IMPUTE_DEBUG") ? 1 : 0;
+    {
+        double ha[MPST_MAX_D], hb[MPST_MAX_D];
+        ha[0] = hb[0] = 0.0;
+        for (int l = 1; l < MPST_MAX_D; l++) { ha[l] = (double)(2 * l - 1) / (double)l; hb[l] = (double)(l - 1) / (double)l; }
+        IMP_TRY(cudaMemcpyToSymbolAsync(c_leg_a, ha, sizeof(ha), 0, cudaMemcpyHostToDevice, c->stream));
+        IMP_TRY(cudaMemcpyToSymbolAsync(c_leg_b, hb, sizeof(hb), 0, cudaMemcpyHostToDevice, c->stream));
+        IMP_TRY(cudaStreamSynchronize(c->stream));                                 // ha/hb are stack temporaries
+    }
     IMP_TRY(cudaFuncSetAttribute(impute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(c, MPST_T_IMPUTE);
     impute_kernel<<<grid, NT, smem, c->stream>>>(P);
