@@ -43,195 +43,249 @@ __global__ void rand_init_kernel(double* __restrict__ Q, int n, int p, int64_t l
 }
 
 // G = sum of `splits` partial Gram matrices (p x p, symmetric positive definite) = L L^T;
-// Rinv = (L^T)^-1 = (L^-1)^T (upper, column-major p x p).  Single CTA, one right-looking pass that factors
-// column k and immediately eliminates it from the running inverse (forward substitution on the identity),
-// two block barriers per column, every update a 2-D thread-parallel rank-1 update in shared memory.
+// Rinv = (L^T)^-1 = (L^-1)^T (upper, column-major p x p), p <= 16 NR.
+// Single CTA of 16 x 16 threads; the whole matrix lives in REGISTERS (thread (ty, tx) owns the NR x NR elements
+// (ty + 16 r, tx + 16 c)), so a column step is one shared-memory broadcast of row k and one block barrier, and
+// the instruction stream per step is ~NR^2 DFMAs plus a short scalar preamble (these kernels are issue-bound,
+// not flop-bound: 8 warps instead of 32 is what makes the step short).
+// Right-looking Cholesky fused with the forward substitution on the identity, in place: after step k the
+// positions (i, j <= k) that held L are dead and take the running inverse X = L^-1, the trailing square
+// (i, j > k) keeps the (full, symmetric) Schur complement, so row k alone carries everything step k needs:
+//     inv = 1/sqrt(m_kk);  l_i = m_ki inv (i > k);  r_j = m_kj inv
+//     m_ij -= l_i r_j (i > k, j != k);  m_ik = -l_i inv (i > k);  m_kj = r_j (j < k);  m_kk = inv.
 // status[0] |= 1 when a pivot is not safely positive (caller falls back to the exact SVD).
+template <int NR>
 __global__ void __launch_bounds__(256)
 chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restrict__ Rinv, int* __restrict__ status) {
-    extern __shared__ double sm[];
-    const int ld = p + 1;
-    double* A = sm;                                    // [p][ld]: lower triangle -> L
-    double* X = sm + (size_t)p * ld;                   // [p][ld]: running B (rows > k) / finished X = L^-1 (rows <= k)
-    __shared__ int s_bad;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    // sum the split-K partials: partial-major so each thread has p*p/256 independent loads in flight
-    for (int e = tid; e < p * p; e += 256) {
-        const int i = e % p, j = e / p;
-        A[i * ld + j] = G[e];
-        X[i * ld + j] = (i == j) ? 1.0 : 0.0;
-    }
-    for (int z = 1; z < splits; z++)
-        for (int e = tid; e < p * p; e += 256) A[(e % p) * ld + e / p] += G[(size_t)z * p * p + e];
-    if (tid == 0) s_bad = 0;
+    __shared__ double rowk[2][128];
+    __shared__ double s_diag[128];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double m[NR][NR];
+    if (threadIdx.x < 128) rowk[0][threadIdx.x] = rowk[1][threadIdx.x] = 0.0;      // tails [p, 128) stay zero
+    // sum the split-K partials (fixed order); both triangles take the lower-triangle value -> exactly symmetric
+#pragma unroll
+    for (int r = 0; r < NR; r++)
+#pragma unroll
+        for (int cc = 0; cc < NR; cc++) {
+            const int i = ty + 16 * r, j = tx + 16 * cc;
+            double v = 0.0;
+            if (i < p && j < p) {
+                const int hi = max(i, j), lo = min(i, j);
+                for (int z = 0; z < splits; z++) v += G[(size_t)z * p * p + hi + (size_t)p * lo];
+                if (i == j) s_diag[i] = v;
+            }
+            m[r][cc] = v;
+        }
     __syncthreads();
     double tr = 0.0;
-    for (int i = 0; i < p; i++) tr = fmax(tr, A[i * ld + i]);
+    for (int i = 0; i < p; i++) tr = fmax(tr, s_diag[i]);
     const double tiny = 1e-13 * tr;                    // kappa(G) beyond ~1e13: CholeskyQR no longer trustworthy
+    bool bad = false;
+#ifdef MPST_KDEBUG
+    const long long tk0 = clock64();
+#endif
     for (int k = 0; k < p; k++) {
-        const double dk = A[k * ld + k];
-        if (tid == 0 && !(dk > tiny)) s_bad = 1;
-        const double inv = rsqrt(fmax(dk, tiny));      // 1 / l_kk
-        __syncthreads();                               // everybody has read the pivot
-        // scale column k of L (rows >= k) and finish row k of X (columns <= k)
-        for (int i = k + tid; i < p; i += 256) A[i * ld + k] *= inv;      // A[k][k] = dk/sqrt(dk) = l_kk
-        for (int j = tid; j <= k; j += 256) X[k * ld + j] *= inv;
-        __syncthreads();
-        // rank-1 updates with column k:  A[i][l] -= L[i][k] L[l][k] (k < l <= i),  B[i][j] -= L[i][k] X[k][j] (j <= k < i)
-        // operands are gathered into registers first so the shared-memory latencies overlap (p <= 112 -> <= 7 per loop)
-        for (int i = k + 1 + ty; i < p; i += 16) {
-            const double lik = A[i * ld + k];
-            double av[7], lv[7], xv[7], kv[7];
+        const int kr = k >> 4, kt = k & 15;
+        double* rk = rowk[k & 1];
+        if (ty == kt) {                                // the half-warp that owns row k publishes it
 #pragma unroll
-            for (int t = 0; t < 7; t++) {
-                const int l = k + 1 + tx + 16 * t;
-                if (l <= i) { av[t] = A[i * ld + l]; lv[t] = A[l * ld + k]; }
-                const int j = tx + 16 * t;
-                if (j <= k) { xv[t] = X[i * ld + j]; kv[t] = X[k * ld + j]; }
-            }
+            for (int r = 0; r < NR; r++)
+                if (r == kr) {
 #pragma unroll
-            for (int t = 0; t < 7; t++) {
-                const int l = k + 1 + tx + 16 * t;
-                if (l <= i) A[i * ld + l] = av[t] - lik * lv[t];
-                const int j = tx + 16 * t;
-                if (j <= k) X[i * ld + j] = xv[t] - lik * kv[t];
-            }
+                    for (int cc = 0; cc < NR; cc++) rk[tx + 16 * cc] = m[r][cc];   // columns >= p hold zeros
+                }
         }
-        // no barrier needed before the next pivot read: A[k+1][k+1] is written by its owner above and the
-        // barrier at the top of the next iteration orders it (pivot is read before that barrier -> add one)
-        __syncthreads();
+        __syncthreads();                               // the only barrier of the step (row buffers alternate)
+        const double dk = rk[k];
+        bad |= !(dk > tiny);
+        const double inv = rsqrt(fmax(dk, tiny));      // 1 / l_kk
+        double li[NR], rj[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) li[r] = (ty + 16 * r > k) ? rk[ty + 16 * r] * inv : 0.0;
+#pragma unroll
+        for (int cc = 0; cc < NR; cc++) rj[cc] = rk[tx + 16 * cc] * inv;
+#pragma unroll
+        for (int r = 0; r < NR; r++)
+#pragma unroll
+            for (int cc = 0; cc < NR; cc++) m[r][cc] = fma(-li[r], rj[cc], m[r][cc]);
+        if (tx == kt) {                                // column k below the pivot: dead L -> X[i][k] = -l_i inv
+#pragma unroll
+            for (int cc = 0; cc < NR; cc++)
+                if (cc == kr) {
+#pragma unroll
+                    for (int r = 0; r < NR; r++)
+                        if (ty + 16 * r > k) m[r][cc] = -li[r] * inv;
+                }
+        }
+        if (ty == kt) {                                // row k: finished row of X (columns > k are dead)
+#pragma unroll
+            for (int r = 0; r < NR; r++)
+                if (r == kr) {
+#pragma unroll
+                    for (int cc = 0; cc < NR; cc++) m[r][cc] = (tx + 16 * cc == k) ? inv : rj[cc];
+                }
+        }
     }
-    for (int e = tid; e < p * p; e += 256) {
-        const int jj = e % p, i = e / p;               // Rinv[jj + p*i] = X[i][jj]  (i >= jj)
-        Rinv[e] = (i >= jj) ? X[i * ld + jj] : 0.0;
-    }
-    if (tid == 0 && s_bad) atomicOr(status, 1);
+#ifdef MPST_KDEBUG
+    if (threadIdx.x == 0) printf("[chol] p=%d splits=%d loop cycles %lld\n", p, splits, clock64() - tk0);
+#endif
+#pragma unroll
+    for (int r = 0; r < NR; r++)
+#pragma unroll
+        for (int cc = 0; cc < NR; cc++) {
+            const int i = ty + 16 * r, j = tx + 16 * cc;                  // Rinv[j + p*i] = X[i][j]  (i >= j)
+            if (i < p && j < p) Rinv[j + (size_t)p * i] = (i >= j) ? m[r][cc] : 0.0;
+        }
+    if (threadIdx.x == 0 && bad) atomicOr(status, 1);
 }
 
-// Eigen-decomposition of a symmetric q x q matrix (embedded in an even order p >= q) by cyclic two-sided
-// Jacobi in shared memory, one CTA.  Per round the p/2 disjoint rotations are computed first, then every
-// 2x2 block (pair I, pair J), I <= J, of A is transformed once with both rotations (B' = R_I^T B R_J) and
-// mirrored, and V's column pairs are rotated: one pass over A (upper half) and V per round, two barriers.
+void launch_chol_inv(int p, const double* G, int splits, double* Rinv, int* status, cudaStream_t st) {
+    switch ((p + 15) / 16) {
+        case 1: chol_inv_kernel<1><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 2: chol_inv_kernel<2><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 3: chol_inv_kernel<3><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 4: chol_inv_kernel<4><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 5: chol_inv_kernel<5><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 6: chol_inv_kernel<6><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 7: chol_inv_kernel<7><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
+        default: chol_inv_kernel<8><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
+    }
+}
+
+// Eigen-decomposition of a symmetric positive semi-definite q x q matrix (a Gram matrix; embedded in an even
+// order p >= q, p <= 16 NT <= 128) by ONE-SIDED (Hestenes) Jacobi on its own columns, one CTA: right rotations J
+// make the columns of H J mutually orthogonal, then H J = W Lambda, i.e. J = W and lambda_i = ||(H J)_i||.
+// A half-warp owns one column pair per round (round-robin ordering, p/2 disjoint pairs, 64 half-warps): it pulls
+// its two columns of H J into registers, forms alpha = |h_a|^2, beta = |h_b|^2, gamma = h_a.h_b with 4 shuffle
+// steps, rotates them and the two columns of J and writes back -- one pass over both matrices and ONE barrier
+// per round; rotation from two rsqrt, no division or sqrt (the kernel is instruction-issue bound).
+// H carries absolute errors ~eps*trace per entry, so gamma is noise below ~eps*trace*max(|h_a|,|h_b|): that
+// is the rotation floor (rotating noise never terminates; the eigenvalues are resolved to eps*trace anyway).
 // W: column-major eigenvectors, ev: eigenvalues (unsorted).  status[1] = sweeps used.
+template <int NT>
 __global__ void __launch_bounds__(1024)
 sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* __restrict__ W, double* __restrict__ ev,
                int* __restrict__ status) {
     extern __shared__ double sm[];
-    const int ld = p + 1, hp = p / 2;
-    double* A = sm;
-    double* V = sm + (size_t)p * ld;
-    double* rc = V + (size_t)p * ld;                   // [hp] cos
-    double* rs = rc + hp;                              // [hp] sin
-    int* rp = reinterpret_cast<int*>(rs + hp);         // [hp] p index, [hp] q index
-    int* rq = rp + hp;
-    __shared__ int any_rot;
-    __shared__ unsigned long long s_maxaa;
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    for (int e = tid; e < p * p; e += nthr) {
-        const int i = e / p, j = e % p;
-        A[i * ld + j] = 0.0;
-        V[i * ld + j] = (i == j) ? 1.0 : 0.0;
+    double* Hc = sm;                                   // [p][p] columns of H J
+    double* Vc = sm + (size_t)p * p;                   // [p][p] columns of J
+    __shared__ int any_rot, any_big;
+    const int tid = threadIdx.x, l16 = tid & 15, hw = tid >> 4, hp = p / 2;
+    for (int e = tid; e < p * p; e += 1024) {          // each (i,j) has one owner and a fixed summation order
+        const int i = e % p, j = e / p;
+        double v = 0.0;
+        if (i < q && j < q)
+            for (int z = 0; z < splits; z++) v += 0.5 * (H[(size_t)z * q * q + i + (size_t)q * j] + H[(size_t)z * q * q + j + (size_t)q * i]);
+        Hc[e] = v;
+        Vc[e] = (i == j) ? 1.0 : 0.0;
     }
-    __syncthreads();
-    for (int z = 0; z < splits; z++)                      // partial-major: independent loads in flight; each (i,j) has
-        for (int e = tid; e < q * q; e += nthr) {         // one owner thread and a fixed summation order (deterministic)
-            const int i = e % q, j = e / q;
-            A[i * ld + j] += 0.5 * (H[(size_t)z * q * q + e] + H[(size_t)z * q * q + j + (size_t)q * i]);
-        }
     __syncthreads();
     double tr = 0.0;
-    for (int i = 0; i < p; i++) tr += A[i * ld + i];
-    // H is a Gram matrix: its entries carry absolute errors ~eps*trace, so couplings below a few eps*trace are
-    // noise (rotating them never terminates); the eigenvalues are resolved to that absolute accuracy anyway.
-    const double floor_abs = 1e-15 * tr;
+    for (int i = 0; i < p; i++) tr += Hc[i * p + i];
+    const double thr2 = (8.9e-16 * tr) * (8.9e-16 * tr);
+    const bool active = hw < hp;
     int sweep = 0;
+#ifdef MPST_KDEBUG
+    const long long tk0 = clock64();
+#endif
     for (; sweep < 60; sweep++) {
-        if (tid == 0) { any_rot = 0; s_maxaa = 0ull; }
+        if (tid == 0) { any_rot = 0; any_big = 0; }
         __syncthreads();
+        // round-robin: half-warp 0 pairs (p-1, rd); half-warp h pairs ((rd+h) mod (p-1), (rd-h) mod (p-1))
+        int a = (hw == 0) ? p - 1 : hw, b = (hw == 0) ? 0 : p - 1 - hw;
         for (int rd = 0; rd < p - 1; rd++) {
-            if (tid < hp) {
-                const int k = tid;
-                int a, b;
-                if (k == 0) { a = p - 1; b = rd; }
-                else { a = (rd + k) % (p - 1); b = (rd - k + (p - 1)) % (p - 1); }
-                const int pp = min(a, b), qq = max(a, b);
-                const double app = A[pp * ld + pp], aqq = A[qq * ld + qq], apq = A[pp * ld + qq];
-                const double aa = fabs(apq);
-                double c = 1.0, sn = 0.0;
-                if (aa > floor_abs && aa * aa > 1e-30 * fabs(app * aqq)) {
-                    // cos/sin of the double angle, then half-angle: two rsqrt, no division
-                    const double zeta = aqq - app, beta = 2.0 * apq;
-                    const double inv_r = rsqrt(zeta * zeta + beta * beta);
-                    const double cos2 = fabs(zeta) * inv_r, sin2 = (zeta >= 0.0 ? beta : -beta) * inv_r;
-                    const double c2 = 0.5 + 0.5 * cos2;
-                    const double inv_c = rsqrt(c2);
-                    c = c2 * inv_c;
-                    sn = 0.5 * sin2 * inv_c;
+            const int ca = active ? min(a, b) : 0, cb = active ? max(a, b) : 1;
+            double* ha = Hc + ca * p;
+            double* hb = Hc + cb * p;
+            double xa[NT], xb[NT];
+            double al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                const int l = l16 + 16 * t;
+                const bool in = active && l < p;
+                xa[t] = in ? ha[l] : 0.0;
+                xb[t] = in ? hb[l] : 0.0;
+                al = fma(xa[t], xa[t], al); be = fma(xb[t], xb[t], be); ga = fma(xa[t], xb[t], ga);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                al += __shfl_xor_sync(0xffffffffu, al, o, 16);
+                be += __shfl_xor_sync(0xffffffffu, be, o, 16);
+                ga += __shfl_xor_sync(0xffffffffu, ga, o, 16);
+            }
+            const double g2 = ga * ga, ab = al * be;
+            if (g2 > thr2 * fmax(al, be) && g2 > 1e-30 * ab) {
+                // cos/sin of the double angle, then half-angle: two rsqrt
+                const double zeta = be - al, beta2 = 2.0 * ga;
+                const double inv_r = rsqrt(zeta * zeta + beta2 * beta2);
+                const double cos2 = fabs(zeta) * inv_r, sin2 = (zeta >= 0.0 ? beta2 : -beta2) * inv_r;
+                const double c2 = 0.5 + 0.5 * cos2;
+                const double inv_c = rsqrt(c2);
+                const double c = c2 * inv_c, sn = 0.5 * sin2 * inv_c;
+                double* va = Vc + ca * p;
+                double* vb = Vc + cb * p;
+#pragma unroll
+                for (int t = 0; t < NT; t++) {
+                    const int l = l16 + 16 * t;
+                    if (l < p) {
+                        ha[l] = c * xa[t] - sn * xb[t];
+                        hb[l] = sn * xa[t] + c * xb[t];
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < NT; t++) {
+                    const int l = l16 + 16 * t;
+                    if (l < p) {
+                        const double ya = va[l], yb = vb[l];
+                        va[l] = c * ya - sn * yb;
+                        vb[l] = sn * ya + c * yb;
+                    }
+                }
+                if (l16 == 0) {
                     any_rot = 1;
-                    atomicMax(&s_maxaa, (unsigned long long)__double_as_longlong(aa));
-                }
-                rc[k] = c; rs[k] = sn; rp[k] = pp; rq[k] = qq;
-            }
-            __syncthreads();
-            // A blocks (I <= J), mirrored.  The upper triangle is folded into a (hp/2) x (hp+1) rectangle (rows I and
-            // hp-1-I share a line) so every thread gets a block; odd hp walks the square and skips I > J.
-            const int nblk = (hp & 1) ? hp * hp : (hp / 2) * (hp + 1);
-            for (int e = tid; e < nblk; e += nthr) {
-                int I, J;
-                if (hp & 1) { I = e / hp; J = e - I * hp; if (I > J) continue; }
-                else {
-                    const int I0 = e / (hp + 1), t = e - I0 * (hp + 1);
-                    if (t < hp - I0) { I = I0; J = I0 + t; }
-                    else { I = hp - 1 - I0; J = I + (t - (hp - I0)); }
-                }
-                const int pi = rp[I], qi = rq[I], pj = rp[J], qj = rq[J];
-                const double ci = rc[I], si = rs[I], cj = rc[J], sj = rs[J];
-                const double b11 = A[pi * ld + pj], b12 = A[pi * ld + qj], b21 = A[qi * ld + pj], b22 = A[qi * ld + qj];
-                // columns: B R_J
-                const double t11 = cj * b11 - sj * b12, t12 = sj * b11 + cj * b12;
-                const double t21 = cj * b21 - sj * b22, t22 = sj * b21 + cj * b22;
-                // rows: R_I^T (.)
-                const double n11 = ci * t11 - si * t21, n12 = ci * t12 - si * t22;
-                const double n21 = si * t11 + ci * t21, n22 = si * t12 + ci * t22;
-                A[pi * ld + pj] = n11; A[pi * ld + qj] = n12; A[qi * ld + pj] = n21; A[qi * ld + qj] = n22;
-                if (I != J) { A[pj * ld + pi] = n11; A[qj * ld + pi] = n12; A[pj * ld + qi] = n21; A[qj * ld + qi] = n22; }
-            }
-            // V column pairs (4 independent element pairs in flight per thread)
-            for (int e0 = tid; e0 < hp * p; e0 += 4 * nthr) {
-                double vx[4], vy[4], cc[4], ss[4];
-                int ip[4], iq[4];
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int e = e0 + t * nthr;
-                    if (e < hp * p) {
-                        const int k = e / p, r = e - k * p;
-                        ip[t] = r * ld + rp[k]; iq[t] = r * ld + rq[k];
-                        cc[t] = rc[k]; ss[t] = rs[k];
-                        vx[t] = V[ip[t]]; vy[t] = V[iq[t]];
-                    }
-                }
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int e = e0 + t * nthr;
-                    if (e < hp * p) {
-                        V[ip[t]] = cc[t] * vx[t] - ss[t] * vy[t];
-                        V[iq[t]] = ss[t] * vx[t] + cc[t] * vy[t];
-                    }
+                    if (g2 > 1e-16 * ab) any_big = 1;             // cosine between the columns above 1e-8
                 }
             }
+            if (hw != 0) a = (a + 1 == p - 1) ? 0 : a + 1;
+            b = (hw == 0) ? b + 1 : ((b + 1 == p - 1) ? 0 : b + 1);
             __syncthreads();
         }
-        // quadratic convergence: a sweep whose largest rotated entry was <= 1e-9*trace leaves <= ~1e-18*trace
-        if (!any_rot || __longlong_as_double((long long)s_maxaa) <= 1e-9 * tr) break;
+        // quadratic convergence: a sweep whose largest rotated cosine was <= 1e-8 leaves cosines at ~1e-16
+        if (!any_rot || !any_big) break;
         __syncthreads();
     }
+#ifdef MPST_KDEBUG
+    if (tid == 0) printf("[eig] p=%d q=%d splits=%d sweeps=%d loop cycles %lld\n", p, q, splits, sweep, clock64() - tk0);
+#endif
     if (tid == 0 && sweep >= 60) atomicOr(status, 2);
     if (tid == 0) status[1] = sweep;
-    for (int e = tid; e < p * p; e += nthr) {
-        const int i = e / p, j = e % p;
-        W[i + (size_t)p * j] = V[i * ld + j];
+    for (int e = tid; e < p * p; e += 1024) W[e] = Vc[e];
+    for (int j = hw; j < p; j += 64) {                 // lambda_j = || (H J)_j ||
+        double nn = 0.0;
+        for (int l = l16; l < p; l += 16) nn += Hc[j * p + l] * Hc[j * p + l];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o, 16);
+        if (l16 == 0) ev[j] = sqrt(nn);
     }
-    for (int i = tid; i < p; i += nthr) ev[i] = A[i * ld + i];
+}
+
+int launch_sym_eig(int p, size_t smem, const double* H, int splits, int q, double* W, double* ev, int* status, cudaStream_t st) {
+#define EIG_CASE(NTV)                                                                                              \
+    case NTV: {                                                                                                    \
+        cudaError_t e = cudaFuncSetAttribute(sym_eig_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return (int)e;                                                                       \
+        sym_eig_kernel<NTV><<<1, 1024, smem, st>>>(H, splits, q, p, W, ev, status);                                \
+    } break;
+    switch ((p + 15) / 16) {
+        EIG_CASE(1) EIG_CASE(2) EIG_CASE(3) EIG_CASE(4) EIG_CASE(5) EIG_CASE(6) EIG_CASE(7)
+        default: {
+            cudaError_t e = cudaFuncSetAttribute(sym_eig_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            sym_eig_kernel<8><<<1, 1024, smem, st>>>(H, splits, q, p, W, ev, status);
+        }
+    }
+#undef EIG_CASE
+    return 0;
 }
 
 // rank the p Ritz values, apply the NDTensors truncation rule with the weight outside the subspace
@@ -372,15 +426,11 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     double* ev = Uk + (size_t)m * k;                                   // p, then Psorted p
     int* status = c->iscal + 8;
     unsigned long long* resbits = reinterpret_cast<unsigned long long*>(c->scal + 10);
-    const size_t chol_smem = 2 * sizeof(double) * (size_t)p * (p + 1);
     const size_t eig_smem = 2 * sizeof(double) * (size_t)p * (p + 1) + sizeof(double) * p + sizeof(int) * p + 16;
-    CUDA_TRY(c, cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
-    CUDA_TRY(c, cudaFuncSetAttribute(sym_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem));
     CUDA_TRY(c, cudaMemsetAsync(status, 0, sizeof(int), c->stream));
     const bool dbg = getenv("MPST_SVD_DEBUG") != nullptr;
     if (dbg) cudaStreamSynchronize(c->stream);
     const auto t0 = std::chrono::steady_clock::now();
-    const unsigned eig_threads = p >= 64 ? 1024u : 256u;
 
     auto finish = [&](const char* what, int iters, double res) -> int {
         *chi_new = c->hiscal[0];
@@ -407,7 +457,7 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         int splits = 1;
         if (mode == 0) TRY(launch_dgemm_splitk(c, 1, 0, q, q, m, M, ldm, M, ldm, Gm, MAXSPLIT, &splits));   // M^T M
         else TRY(launch_dgemm_splitk(c, 0, 1, q, q, n, M, ldm, M, ldm, Gm, MAXSPLIT, &splits));            // M M^T
-        sym_eig_kernel<<<1, eig_threads, eig_smem, c->stream>>>(Gm, splits, q, p, Wm, ev, status);
+        if (launch_sym_eig(p, eig_smem, Gm, splits, q, Wm, ev, status, c->stream)) CUDA_TRY(c, cudaGetLastError());
         ritz_trunc_kernel<<<1, 256, 0, c->stream>>>(ev, p, q, trace_dev, chi_max, cutoff, c->perm, ev + p, c->iscal);
         gather_cols_kernel<<<(p * k + 255) / 256, 256, 0, c->stream>>>(Wm, p, c->perm, k, Wk);
         c->launches += 3;
@@ -439,7 +489,7 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     auto cholqr = [&](double* X, double* out, int rows) -> int {
         int splits = 1;
         TRY(launch_dgemm_splitk(c, 1, 0, p, p, rows, X, rows, X, rows, Gm, MAXSPLIT, &splits));
-        chol_inv_kernel<<<1, 256, chol_smem, c->stream>>>(Gm, splits, p, Ri, status);
+        launch_chol_inv(p, Gm, splits, Ri, status, c->stream);
         c->launches++;
         TRY(launch_dgemm(c, 0, 0, rows, p, p, X, rows, Ri, p, out, rows));
         return MPST_OK;
@@ -449,8 +499,8 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         rand_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(Qa, n, p, n, 0x5DEECE66Dull + (uint64_t)m * 131 + n);
         c->launches++;
     }
-    TRY(cholqr(Qa, Qb, n));
-    TRY(cholqr(Qb, Qa, n));                                            // Q = Qa
+    // the random start needs no orthonormalisation: an n x p matrix of iid entries is well conditioned
+    // (kappa ~ (sqrt(n)+sqrt(p))/(sqrt(n)-sqrt(p))) and only its span matters
     const int max_rounds = 3;
     int iters_done = 0;
     for (int round = 0; round < max_rounds; round++) {
@@ -468,7 +518,7 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         int splits = 1;
         TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, Qa, n, Za, m));                // Z = M Q
         TRY(launch_dgemm_splitk(c, 1, 0, p, p, m, Za, m, Za, m, Gm, MAXSPLIT, &splits));   // H = Z^T Z
-        sym_eig_kernel<<<1, eig_threads, eig_smem, c->stream>>>(Gm, splits, p, p, Wm, ev, status);
+        if (launch_sym_eig(p, eig_smem, Gm, splits, p, Wm, ev, status, c->stream)) CUDA_TRY(c, cudaGetLastError());
         ritz_trunc_kernel<<<1, 256, 0, c->stream>>>(ev, p, n, trace_dev, chi_max, cutoff, c->perm, ev + p, c->iscal);
         gather_cols_kernel<<<(p * k + 255) / 256, 256, 0, c->stream>>>(Wm, p, c->perm, k, Wk);
         c->launches += 3;
