@@ -162,13 +162,14 @@ void launch_chol_inv(int p, const double* G, int splits, double* Rinv, int* stat
 // H carries absolute errors ~eps*trace per entry, so gamma is noise below ~eps*trace*max(|h_a|,|h_b|): that
 // is the rotation floor (rotating noise never terminates; the eigenvalues are resolved to eps*trace anyway).
 // W: column-major eigenvectors, ev: eigenvalues (unsorted).  status[1] = sweeps used.
-template <int NT>
+template <int NT, bool FULL>
 __global__ void __launch_bounds__(1024)
 sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* __restrict__ W, double* __restrict__ ev,
                int* __restrict__ status) {
     extern __shared__ double sm[];
     double* Hc = sm;                                   // [p][p] columns of H J
     double* Vc = sm + (size_t)p * p;                   // [p][p] columns of J
+    double* nrm = Vc + (size_t)p * p;                  // [p] cached squared column norms of H J
     __shared__ int any_rot, any_big;
     const int tid = threadIdx.x, l16 = tid & 15, hw = tid >> 4, hp = p / 2;
     for (int e = tid; e < p * p; e += 1024) {          // each (i,j) has one owner and a fixed summation order
@@ -184,66 +185,71 @@ sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* _
     for (int i = 0; i < p; i++) tr += Hc[i * p + i];
     const double thr2 = (8.9e-16 * tr) * (8.9e-16 * tr);
     const bool active = hw < hp;
+    const bool warp_active = (tid >> 5) * 2 < hp;      // warps without a pair only take part in the barriers
     int sweep = 0;
 #ifdef MPST_KDEBUG
     const long long tk0 = clock64();
 #endif
     for (; sweep < 60; sweep++) {
         if (tid == 0) { any_rot = 0; any_big = 0; }
+        // squared column norms, recomputed from the columns once per sweep and updated by the rotations in between
+        // (they only steer the rotation; the eigenvalues are taken from the columns themselves at the end)
+        for (int j = hw; j < p; j += 64) {
+            double nn = 0.0;
+            for (int l = l16; l < p; l += 16) nn = fma(Hc[j * p + l], Hc[j * p + l], nn);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o, 16);
+            if (l16 == 0) nrm[j] = nn;
+        }
         __syncthreads();
         // round-robin: half-warp 0 pairs (p-1, rd); half-warp h pairs ((rd+h) mod (p-1), (rd-h) mod (p-1))
         int a = (hw == 0) ? p - 1 : hw, b = (hw == 0) ? 0 : p - 1 - hw;
         for (int rd = 0; rd < p - 1; rd++) {
-            const int ca = active ? min(a, b) : 0, cb = active ? max(a, b) : 1;
-            double* ha = Hc + ca * p;
-            double* hb = Hc + cb * p;
-            double xa[NT], xb[NT];
-            double al = 0.0, be = 0.0, ga = 0.0;
-#pragma unroll
-            for (int t = 0; t < NT; t++) {
-                const int l = l16 + 16 * t;
-                const bool in = active && l < p;
-                xa[t] = in ? ha[l] : 0.0;
-                xb[t] = in ? hb[l] : 0.0;
-                al = fma(xa[t], xa[t], al); be = fma(xb[t], xb[t], be); ga = fma(xa[t], xb[t], ga);
-            }
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                al += __shfl_xor_sync(0xffffffffu, al, o, 16);
-                be += __shfl_xor_sync(0xffffffffu, be, o, 16);
-                ga += __shfl_xor_sync(0xffffffffu, ga, o, 16);
-            }
-            const double g2 = ga * ga, ab = al * be;
-            if (g2 > thr2 * fmax(al, be) && g2 > 1e-30 * ab) {
-                // cos/sin of the double angle, then half-angle: two rsqrt
-                const double zeta = be - al, beta2 = 2.0 * ga;
-                const double inv_r = rsqrt(zeta * zeta + beta2 * beta2);
-                const double cos2 = fabs(zeta) * inv_r, sin2 = (zeta >= 0.0 ? beta2 : -beta2) * inv_r;
-                const double c2 = 0.5 + 0.5 * cos2;
-                const double inv_c = rsqrt(c2);
-                const double c = c2 * inv_c, sn = 0.5 * sin2 * inv_c;
-                double* va = Vc + ca * p;
-                double* vb = Vc + cb * p;
+            if (warp_active) {
+                const int ca = active ? min(a, b) : 0, cb = active ? max(a, b) : 1;
+                double* ha = Hc + ca * p + l16;
+                double* hb = Hc + cb * p + l16;
+                double xa[NT], xb[NT];
+                double ga = 0.0;
 #pragma unroll
                 for (int t = 0; t < NT; t++) {
-                    const int l = l16 + 16 * t;
-                    if (l < p) {
-                        ha[l] = c * xa[t] - sn * xb[t];
-                        hb[l] = sn * xa[t] + c * xb[t];
-                    }
+                    const bool in = FULL || (l16 + 16 * t < p);
+                    xa[t] = in ? ha[16 * t] : 0.0;
+                    xb[t] = in ? hb[16 * t] : 0.0;
+                    ga = fma(xa[t], xb[t], ga);
                 }
+                const double al = nrm[ca], be = nrm[cb];
 #pragma unroll
-                for (int t = 0; t < NT; t++) {
-                    const int l = l16 + 16 * t;
-                    if (l < p) {
-                        const double ya = va[l], yb = vb[l];
-                        va[l] = c * ya - sn * yb;
-                        vb[l] = sn * ya + c * yb;
+                for (int o = 8; o > 0; o >>= 1) ga += __shfl_xor_sync(0xffffffffu, ga, o, 16);
+                const double g2 = ga * ga, ab = al * be;
+                if (active && g2 > thr2 * fmax(al, be) && g2 > 1e-30 * ab) {
+                    // cos/sin of the double angle, then half-angle: two rsqrt
+                    const double zeta = be - al, beta2 = 2.0 * ga;
+                    const double inv_r = rsqrt(zeta * zeta + beta2 * beta2);
+                    const double cos2 = fabs(zeta) * inv_r, sin2 = (zeta >= 0.0 ? beta2 : -beta2) * inv_r;
+                    const double c2 = 0.5 + 0.5 * cos2;
+                    const double inv_c = rsqrt(c2);
+                    const double c = c2 * inv_c, sn = 0.5 * sin2 * inv_c;
+                    double* va = Vc + ca * p + l16;
+                    double* vb = Vc + cb * p + l16;
+#pragma unroll
+                    for (int t = 0; t < NT; t++) {
+                        if (FULL || (l16 + 16 * t < p)) {
+                            const double ya = va[16 * t], yb = vb[16 * t];
+                            ha[16 * t] = c * xa[t] - sn * xb[t];
+                            hb[16 * t] = sn * xa[t] + c * xb[t];
+                            va[16 * t] = c * ya - sn * yb;
+                            vb[16 * t] = sn * ya + c * yb;
+                        }
                     }
-                }
-                if (l16 == 0) {
-                    any_rot = 1;
-                    if (g2 > 1e-16 * ab) any_big = 1;             // cosine between the columns above 1e-8
+                    if (l16 == 0) {
+                        // |h_a'|^2 = c^2 al - 2cs ga + s^2 be,  |h_b'|^2 = s^2 al + 2cs ga + c^2 be
+                        const double cs2 = 2.0 * c * sn * ga, cc = c * c, ss = sn * sn;
+                        nrm[ca] = cc * al - cs2 + ss * be;
+                        nrm[cb] = ss * al + cs2 + cc * be;
+                        any_rot = 1;
+                        if (g2 > 1e-16 * ab) any_big = 1;         // cosine between the columns above 1e-8
+                    }
                 }
             }
             if (hw != 0) a = (a + 1 == p - 1) ? 0 : a + 1;
@@ -269,23 +275,31 @@ sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* _
     }
 }
 
-int launch_sym_eig(int p, size_t smem, const double* H, int splits, int q, double* W, double* ev, int* status, cudaStream_t st) {
-#define EIG_CASE(NTV)                                                                                              \
-    case NTV: {                                                                                                    \
-        cudaError_t e = cudaFuncSetAttribute(sym_eig_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return (int)e;                                                                       \
-        sym_eig_kernel<NTV><<<1, 1024, smem, st>>>(H, splits, q, p, W, ev, status);                                \
-    } break;
-    switch ((p + 15) / 16) {
-        EIG_CASE(1) EIG_CASE(2) EIG_CASE(3) EIG_CASE(4) EIG_CASE(5) EIG_CASE(6) EIG_CASE(7)
-        default: {
-            cudaError_t e = cudaFuncSetAttribute(sym_eig_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            sym_eig_kernel<8><<<1, 1024, smem, st>>>(H, splits, q, p, W, ev, status);
-        }
+template <int NT>
+int launch_sym_eig_nt(int p, size_t smem, const double* H, int splits, int q, double* W, double* ev, int* status, cudaStream_t st) {
+    if (p % 16 == 0) {
+        cudaError_t e = cudaFuncSetAttribute(sym_eig_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        sym_eig_kernel<NT, true><<<1, 1024, smem, st>>>(H, splits, q, p, W, ev, status);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(sym_eig_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        sym_eig_kernel<NT, false><<<1, 1024, smem, st>>>(H, splits, q, p, W, ev, status);
     }
-#undef EIG_CASE
     return 0;
+}
+
+int launch_sym_eig(int p, size_t smem, const double* H, int splits, int q, double* W, double* ev, int* status, cudaStream_t st) {
+    switch ((p + 15) / 16) {
+        case 1: return launch_sym_eig_nt<1>(p, smem, H, splits, q, W, ev, status, st);
+        case 2: return launch_sym_eig_nt<2>(p, smem, H, splits, q, W, ev, status, st);
+        case 3: return launch_sym_eig_nt<3>(p, smem, H, splits, q, W, ev, status, st);
+        case 4: return launch_sym_eig_nt<4>(p, smem, H, splits, q, W, ev, status, st);
+        case 5: return launch_sym_eig_nt<5>(p, smem, H, splits, q, W, ev, status, st);
+        case 6: return launch_sym_eig_nt<6>(p, smem, H, splits, q, W, ev, status, st);
+        case 7: return launch_sym_eig_nt<7>(p, smem, H, splits, q, W, ev, status, st);
+        default: return launch_sym_eig_nt<8>(p, smem, H, splits, q, W, ev, status, st);
+    }
 }
 
 // rank the p Ritz values, apply the NDTensors truncation rule with the weight outside the subspace
