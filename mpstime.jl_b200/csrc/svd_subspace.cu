@@ -54,28 +54,52 @@ __global__ void rand_init_kernel(double* __restrict__ Q, int n, int p, int64_t l
 //     inv = 1/sqrt(m_kk);  l_i = m_ki inv (i > k);  r_j = m_kj inv
 //     m_ij -= l_i r_j (i > k, j != k);  m_ik = -l_i inv (i > k);  m_kj = r_j (j < k);  m_kk = inv.
 // status[0] |= 1 when a pivot is not safely positive (caller falls back to the exact SVD).
-template <int NR>
-__global__ void __launch_bounds__(256)
+template <int NRR, int NRC, int TYN>
+__global__ void __launch_bounds__(TYN * 16)
 chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restrict__ Rinv, int* __restrict__ status) {
     __shared__ double rowk[2][128];
     __shared__ double s_diag[128];
+    constexpr int NTHR = TYN * 16;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double m[NR][NR];
-    if (threadIdx.x < 128) rowk[0][threadIdx.x] = rowk[1][threadIdx.x] = 0.0;      // tails [p, 128) stay zero
-    // sum the split-K partials (fixed order); both triangles take the lower-triangle value -> exactly symmetric
+    double m[NRR][NRC];
+#ifdef MPST_KDEBUG
+    const long long tk00 = clock64();
+#endif
+    for (int t = threadIdx.x; t < 256; t += NTHR) (&rowk[0][0])[t] = 0.0;          // tails [p, 128) stay zero
+    // sum the split-K partials (fixed order, partial-major so a thread has all its loads of one partial in flight).
+    // The Gram partials are symmetric (a*b == b*a, same accumulation order in both triangles), so the transposed,
+    // coalesced read is the same matrix.
 #pragma unroll
-    for (int r = 0; r < NR; r++)
+    for (int r = 0; r < NRR; r++)
 #pragma unroll
-        for (int cc = 0; cc < NR; cc++) {
-            const int i = ty + 16 * r, j = tx + 16 * cc;
-            double v = 0.0;
-            if (i < p && j < p) {
-                const int hi = max(i, j), lo = min(i, j);
-                for (int z = 0; z < splits; z++) v += G[(size_t)z * p * p + hi + (size_t)p * lo];
-                if (i == j) s_diag[i] = v;
-            }
-            m[r][cc] = v;
-        }
+        for (int cc = 0; cc < NRC; cc++) m[r][cc] = 0.0;
+    int roff[NRR], coff[NRC];                          // clamped -> unconditional loads that batch (one latency per partial)
+#pragma unroll
+    for (int r = 0; r < NRR; r++) roff[r] = p * min(ty + TYN * r, p - 1);
+#pragma unroll
+    for (int cc = 0; cc < NRC; cc++) coff[cc] = min(tx + 16 * cc, p - 1);
+    for (int z = 0; z < splits; z++) {
+        const double* gz = G + (size_t)z * p * p;
+        double v[NRR][NRC];
+#pragma unroll
+        for (int r = 0; r < NRR; r++)
+#pragma unroll
+            for (int cc = 0; cc < NRC; cc++) v[r][cc] = gz[roff[r] + coff[cc]];    // (j, i): coalesced along tx
+#pragma unroll
+        for (int r = 0; r < NRR; r++)
+#pragma unroll
+            for (int cc = 0; cc < NRC; cc++) m[r][cc] += v[r][cc];
+    }
+#pragma unroll
+    for (int r = 0; r < NRR; r++)
+#pragma unroll
+        for (int cc = 0; cc < NRC; cc++)
+            if (ty + TYN * r >= p || tx + 16 * cc >= p) m[r][cc] = 0.0;
+#pragma unroll
+    for (int r = 0; r < NRR; r++)
+#pragma unroll
+        for (int cc = 0; cc < NRC; cc++)
+            if (ty + TYN * r == tx + 16 * cc && ty + TYN * r < p) s_diag[ty + TYN * r] = m[r][cc];
     __syncthreads();
     double tr = 0.0;
     for (int i = 0; i < p; i++) tr = fmax(tr, s_diag[i]);
@@ -84,71 +108,75 @@ chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restr
 #ifdef MPST_KDEBUG
     const long long tk0 = clock64();
 #endif
-    for (int k = 0; k < p; k++) {
-        const int kr = k >> 4, kt = k & 15;
-        double* rk = rowk[k & 1];
-        if (ty == kt) {                                // the half-warp that owns row k publishes it
+    // The pivot loop is unrolled over the (row slot, column slot) that holds the pivot, so every register index is
+    // a compile-time constant (no jump tables) and the finished row slots above the pivot drop out of the update.
+    constexpr int HS = 16 / TYN;                       // row slots per 16-column block (2 for TYN = 8)
 #pragma unroll
-            for (int r = 0; r < NR; r++)
-                if (r == kr) {
+    for (int kb = 0; kb < NRC; kb++) {
 #pragma unroll
-                    for (int cc = 0; cc < NR; cc++) rk[tx + 16 * cc] = m[r][cc];   // columns >= p hold zeros
+        for (int h = 0; h < HS; h++) {
+            const int krr = kb * HS + h;               // row slot of the pivots k0 .. k0 + TYN - 1
+            const int k0 = 16 * kb + TYN * h;
+            const int kend = min(TYN, p - k0);
+#pragma unroll 1
+            for (int kt = 0; kt < kend; kt++) {
+                const int k = k0 + kt;
+                double* rk = &rowk[k & 1][0];
+                if (ty == kt) {                        // the 16 threads that own row k publish it
+#pragma unroll
+                    for (int cc = 0; cc < NRC; cc++) rk[tx + 16 * cc] = m[krr][cc];   // columns >= p hold zeros
                 }
-        }
-        __syncthreads();                               // the only barrier of the step (row buffers alternate)
-        const double dk = rk[k];
-        bad |= !(dk > tiny);
-        const double inv = rsqrt(fmax(dk, tiny));      // 1 / l_kk
-        double li[NR], rj[NR];
+                __syncthreads();                       // the only barrier of the step (row buffers alternate)
+                const double dk = rk[k];
+                bad |= !(dk > tiny);
+                const double inv = rsqrt(dk > tiny ? dk : tiny);      // 1 / l_kk
+                double li[NRR], rj[NRC];
 #pragma unroll
-        for (int r = 0; r < NR; r++) li[r] = (ty + 16 * r > k) ? rk[ty + 16 * r] * inv : 0.0;
-#pragma unroll
-        for (int cc = 0; cc < NR; cc++) rj[cc] = rk[tx + 16 * cc] * inv;
-#pragma unroll
-        for (int r = 0; r < NR; r++)
-#pragma unroll
-            for (int cc = 0; cc < NR; cc++) m[r][cc] = fma(-li[r], rj[cc], m[r][cc]);
-        if (tx == kt) {                                // column k below the pivot: dead L -> X[i][k] = -l_i inv
-#pragma unroll
-            for (int cc = 0; cc < NR; cc++)
-                if (cc == kr) {
-#pragma unroll
-                    for (int r = 0; r < NR; r++)
-                        if (ty + 16 * r > k) m[r][cc] = -li[r] * inv;
+                for (int r = krr; r < NRR; r++) {
+                    const double v = rk[ty + TYN * r] * inv;          // every index < 128 is initialised
+                    li[r] = (r > krr || ty > kt) ? v : 0.0;           // rows at or above the pivot do not move
                 }
-        }
-        if (ty == kt) {                                // row k: finished row of X (columns > k are dead)
 #pragma unroll
-            for (int r = 0; r < NR; r++)
-                if (r == kr) {
+                for (int cc = 0; cc < NRC; cc++) rj[cc] = rk[tx + 16 * cc] * inv;
 #pragma unroll
-                    for (int cc = 0; cc < NR; cc++) m[r][cc] = (tx + 16 * cc == k) ? inv : rj[cc];
+                for (int r = krr; r < NRR; r++)
+#pragma unroll
+                    for (int cc = 0; cc < NRC; cc++) m[r][cc] = fma(-li[r], rj[cc], m[r][cc]);
+                const bool col_owner = tx == TYN * h + kt;            // column k below the pivot: dead L -> X[i][k]
+#pragma unroll
+                for (int r = krr; r < NRR; r++) m[r][kb] = (col_owner && (r > krr || ty > kt)) ? -li[r] * inv : m[r][kb];
+                if (ty == kt) {                        // row k: finished row of X (columns > k are dead)
+#pragma unroll
+                    for (int cc = 0; cc < NRC; cc++) m[krr][cc] = (cc == kb && col_owner) ? inv : rj[cc];
                 }
+            }
         }
     }
 #ifdef MPST_KDEBUG
-    if (threadIdx.x == 0) printf("[chol] p=%d splits=%d loop cycles %lld\n", p, splits, clock64() - tk0);
+    if (threadIdx.x == 0) printf("[chol] p=%d splits=%d loop cycles %lld  since start %lld\n", p, splits, clock64() - tk0, clock64() - tk00);
 #endif
 #pragma unroll
-    for (int r = 0; r < NR; r++)
+    for (int r = 0; r < NRR; r++)
 #pragma unroll
-        for (int cc = 0; cc < NR; cc++) {
-            const int i = ty + 16 * r, j = tx + 16 * cc;                  // Rinv[j + p*i] = X[i][j]  (i >= j)
+        for (int cc = 0; cc < NRC; cc++) {
+            const int i = ty + TYN * r, j = tx + 16 * cc;                 // Rinv[j + p*i] = X[i][j]  (i >= j)
             if (i < p && j < p) Rinv[j + (size_t)p * i] = (i >= j) ? m[r][cc] : 0.0;
         }
     if (threadIdx.x == 0 && bad) atomicOr(status, 1);
 }
 
+// p <= 96: 4 warps (8 x 16 threads, 2NC x NC register tile) -- these kernels are issue/latency bound and the
+// per-thread scalar preamble dominates, so fewer, fatter threads win; larger p: 8 warps (register budget).
 void launch_chol_inv(int p, const double* G, int splits, double* Rinv, int* status, cudaStream_t st) {
     switch ((p + 15) / 16) {
-        case 1: chol_inv_kernel<1><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
-        case 2: chol_inv_kernel<2><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
-        case 3: chol_inv_kernel<3><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
-        case 4: chol_inv_kernel<4><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
-        case 5: chol_inv_kernel<5><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
-        case 6: chol_inv_kernel<6><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
-        case 7: chol_inv_kernel<7><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
-        default: chol_inv_kernel<8><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 1: chol_inv_kernel<2, 1, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 2: chol_inv_kernel<4, 2, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 3: chol_inv_kernel<6, 3, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 4: chol_inv_kernel<8, 4, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 5: chol_inv_kernel<10, 5, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 6: chol_inv_kernel<12, 6, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 7: chol_inv_kernel<7, 7, 16><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
+        default: chol_inv_kernel<8, 8, 16><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
     }
 }
 
@@ -172,13 +200,23 @@ sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* _
     double* nrm = Vc + (size_t)p * p;                  // [p] cached squared column norms of H J
     __shared__ int any_rot, any_big;
     const int tid = threadIdx.x, l16 = tid & 15, hw = tid >> 4, hp = p / 2;
-    for (int e = tid; e < p * p; e += 1024) {          // each (i,j) has one owner and a fixed summation order
+    // sum the split-K partials with coalesced reads (fixed order per element), then symmetrise in shared memory
+    for (int e = tid; e < p * p; e += 1024) {
         const int i = e % p, j = e / p;
         double v = 0.0;
         if (i < q && j < q)
-            for (int z = 0; z < splits; z++) v += 0.5 * (H[(size_t)z * q * q + i + (size_t)q * j] + H[(size_t)z * q * q + j + (size_t)q * i]);
+            for (int z = 0; z < splits; z++) v += H[(size_t)z * q * q + i + (size_t)q * j];
         Hc[e] = v;
         Vc[e] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < p * p; e += 1024) {
+        const int i = e % p, j = e / p;
+        if (i < j) {
+            const double v = 0.5 * (Hc[i + p * j] + Hc[j + p * i]);
+            Hc[i + p * j] = v;
+            Hc[j + p * i] = v;
+        }
     }
     __syncthreads();
     double tr = 0.0;
