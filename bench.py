@@ -226,6 +226,19 @@ def impute_bench(m, ctx, args):
 
 
 # ------------------------------------------------------------------------------------------------
+def pinned_copy(a):
+    """numpy view of a page-locked copy of `a` (torch is only the pinned allocator here)."""
+    import torch
+    t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+    out = t.numpy()
+    out[...] = a
+    _PINNED.append(t)
+    return out
+
+
+_PINNED = []
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -296,13 +309,22 @@ def main():
     cores_host = ctx.get_cores()
     h2d = Xs_sorted.nbytes + sum(c.nbytes for c in cores_host)
     d2h = sum(c.nbytes for c in cores_host) + 2 * (T - 1) * 20
+    # the step's input lives in pinned host memory, already in the wire layout (Julia column-major T x N == C-order
+    # (N, T)), so train_load_x hands the pinned pointer straight to the C ABI (no host-side transpose)
+    X_pinned = pinned_copy(np.ascontiguousarray(Xs_sorted.T)).T
+
+    def e2e_step(cores):
+        ctx.train_load_x(X_pinned, counts, d, chi_max, n_global=N_global, counts_global=counts_global)
+        ctx.set_cores(cores)
+        ctx.sweep(topts, 1, record=True)
+        return ctx.get_cores()
+
+    if args.warmup:
+        cores_host = e2e_step(cores_host)              # untimed: first-touch of the pinned buffer, allocator state
     barrier(td, local)
     t0 = time.time()
     for _ in range(args.steps):
-        ctx.train_load_x(Xs_sorted, counts, d, chi_max, n_global=N_global, counts_global=counts_global)
-        ctx.set_cores(cores_host)
-        ctx.sweep(topts, 1, record=True)
-        cores_host = ctx.get_cores()
+        cores_host = e2e_step(cores_host)
     barrier(td, local)
     e2e_s = max_over_ranks(td, local, time.time() - t0)
     e2e = sample_bonds / e2e_s

@@ -16,7 +16,7 @@ namespace {
 constexpr int KC = 16, LDP = KC + 4;
 
 template <int TM, int TN, int WM, int WN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, (TN <= 80 ? 2 : 1))
 krao_gemm_kernel(const double* __restrict__ x, const double* __restrict__ E,
                  const double* __restrict__ W, double* __restrict__ out, int64_t row_begin,
                  int64_t row_end, int d, int chi, int n_out, int64_t ldw, int64_t ldo) {
@@ -137,6 +137,7 @@ int launch_cfg(mpst_ctx* c, const double* x, const double* E, const double* W, d
     const size_t smem = 16 + sizeof(double) * ((size_t)TM * chi + (size_t)TM * d + 2 * TM * LDP + 2 * TN * LDP);
     auto kern = krao_gemm_kernel<TM, TN, WM, WN>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int64_t t0 = row_begin / TM, t1 = (row_end + TM - 1) / TM;
     dim3 grid((unsigned)(t1 - t0), (unsigned)((n_out + TN - 1) / TN));
     kern<<<grid, 256, smem, c->stream>>>(x, E, W, out, row_begin, row_end, d, chi, n_out, ldw, ldo);
@@ -162,6 +163,8 @@ int launch_krao_gemm_rows(mpst_ctx* c, const double* x, const double* E, const d
         if (n_out <= 32) return launch_cfg<128, 32, 8, 1>(ARGS);
         if (n_out <= 48) return launch_cfg<128, 48, 4, 2>(ARGS);       // chi = 40 (config B): 17% padding instead of 37%
         if (n_out <= 64) return launch_cfg<128, 64, 4, 2>(ARGS);
+        if (n_out <= 80) return launch_cfg<128, 80, 4, 2>(ARGS);       // chi*C = 80 (config B, labelled core)
+        if (n_out <= 96) return launch_cfg<128, 96, 4, 2>(ARGS);
         return launch_cfg<128, 128, 4, 2>(ARGS);
     }
     if (n_out <= 8) return launch_cfg<64, 8, 8, 1>(ARGS);

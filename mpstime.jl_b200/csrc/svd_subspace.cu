@@ -56,7 +56,8 @@ __global__ void rand_init_kernel(double* __restrict__ Q, int n, int p, int64_t l
 // status[0] |= 1 when a pivot is not safely positive (caller falls back to the exact SVD).
 template <int NRR, int NRC, int TYN>
 __global__ void __launch_bounds__(TYN * 16)
-chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restrict__ Rinv, int* __restrict__ status) {
+chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restrict__ Rinv, double* __restrict__ Lout,
+                int* __restrict__ status) {
     __shared__ double rowk[2][128];
     __shared__ double s_diag[128];
     constexpr int NTHR = TYN * 16;
@@ -143,6 +144,13 @@ chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restr
 #pragma unroll
                     for (int cc = 0; cc < NRC; cc++) m[r][cc] = fma(-li[r], rj[cc], m[r][cc]);
                 const bool col_owner = tx == TYN * h + kt;            // column k below the pivot: dead L -> X[i][k]
+                if (Lout != nullptr && col_owner) {                   // column k of L (diagonal = sqrt(d_k)), rows >= slot start
+#pragma unroll
+                    for (int r = krr; r < NRR; r++) {
+                        const int i = ty + TYN * r;
+                        if (i < p) Lout[i + (size_t)p * k] = (r == krr && ty == kt) ? dk * inv : li[r];
+                    }
+                }
 #pragma unroll
                 for (int r = krr; r < NRR; r++) m[r][kb] = (col_owner && (r > krr || ty > kt)) ? -li[r] * inv : m[r][kb];
                 if (ty == kt) {                        // row k: finished row of X (columns > k are dead)
@@ -167,16 +175,16 @@ chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restr
 
 // p <= 96: 4 warps (8 x 16 threads, 2NC x NC register tile) -- these kernels are issue/latency bound and the
 // per-thread scalar preamble dominates, so fewer, fatter threads win; larger p: 8 warps (register budget).
-void launch_chol_inv(int p, const double* G, int splits, double* Rinv, int* status, cudaStream_t st) {
+void launch_chol_inv(int p, const double* G, int splits, double* Rinv, double* Lout, int* status, cudaStream_t st) {
     switch ((p + 15) / 16) {
-        case 1: chol_inv_kernel<2, 1, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, status); break;
-        case 2: chol_inv_kernel<4, 2, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, status); break;
-        case 3: chol_inv_kernel<6, 3, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, status); break;
-        case 4: chol_inv_kernel<8, 4, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, status); break;
-        case 5: chol_inv_kernel<10, 5, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, status); break;
-        case 6: chol_inv_kernel<12, 6, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, status); break;
-        case 7: chol_inv_kernel<7, 7, 16><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
-        default: chol_inv_kernel<8, 8, 16><<<1, 256, 0, st>>>(G, splits, p, Rinv, status); break;
+        case 1: chol_inv_kernel<2, 1, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, Lout, status); break;
+        case 2: chol_inv_kernel<4, 2, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, Lout, status); break;
+        case 3: chol_inv_kernel<6, 3, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, Lout, status); break;
+        case 4: chol_inv_kernel<8, 4, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, Lout, status); break;
+        case 5: chol_inv_kernel<10, 5, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, Lout, status); break;
+        case 6: chol_inv_kernel<12, 6, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, Lout, status); break;
+        case 7: chol_inv_kernel<7, 7, 16><<<1, 256, 0, st>>>(G, splits, p, Rinv, Lout, status); break;
+        default: chol_inv_kernel<8, 8, 16><<<1, 256, 0, st>>>(G, splits, p, Rinv, Lout, status); break;
     }
 }
 
@@ -190,7 +198,7 @@ void launch_chol_inv(int p, const double* G, int splits, double* Rinv, int* stat
 // H carries absolute errors ~eps*trace per entry, so gamma is noise below ~eps*trace*max(|h_a|,|h_b|): that
 // is the rotation floor (rotating noise never terminates; the eigenvalues are resolved to eps*trace anyway).
 // W: column-major eigenvectors, ev: eigenvalues (unsorted).  status[1] = sweeps used.
-template <int NT, bool FULL>
+template <int NT, bool FULL, bool LMODE>
 __global__ void __launch_bounds__(1024)
 sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* __restrict__ W, double* __restrict__ ev,
                int* __restrict__ status) {
@@ -199,29 +207,55 @@ sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* _
     double* Vc = sm + (size_t)p * p;                   // [p][p] columns of J
     double* nrm = Vc + (size_t)p * p;                  // [p] cached squared column norms of H J
     __shared__ int any_rot, any_big;
+#ifdef MPST_KDEBUG
+    __shared__ int dbg_rot, dbg_big;
+    __shared__ unsigned long long dbg_max;
+    if (threadIdx.x == 0) { dbg_rot = 0; dbg_big = 0; dbg_max = 0ull; }
+#endif
     const int tid = threadIdx.x, l16 = tid & 15, hw = tid >> 4, hp = p / 2;
-    // sum the split-K partials with coalesced reads (fixed order per element), then symmetrise in shared memory
-    for (int e = tid; e < p * p; e += 1024) {
-        const int i = e % p, j = e / p;
-        double v = 0.0;
-        if (i < q && j < q)
-            for (int z = 0; z < splits; z++) v += H[(size_t)z * q * q + i + (size_t)q * j];
-        Hc[e] = v;
-        Vc[e] = (i == j) ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    for (int e = tid; e < p * p; e += 1024) {
-        const int i = e % p, j = e / p;
-        if (i < j) {
-            const double v = 0.5 * (Hc[i + p * j] + Hc[j + p * i]);
-            Hc[i + p * j] = v;
-            Hc[j + p * i] = v;
-        }
-    }
-    __syncthreads();
     double tr = 0.0;
-    for (int i = 0; i < p; i++) tr += Hc[i * p + i];
-    const double thr2 = (8.9e-16 * tr) * (8.9e-16 * tr);
+    if (LMODE) {
+        // H is the lower Cholesky factor L of the matrix to decompose (L L^T = W Lambda W^T): Jacobi on the columns of
+        // L gives L J = W Sigma, no rotation accumulator needed; trace(L L^T) = ||L||_F^2
+        for (int e = tid; e < p * p; e += 1024) {
+            const int i = e % p, j = e / p;
+            Hc[e] = (i >= j) ? H[e] : 0.0;
+        }
+        __syncthreads();
+        for (int j = hw; j < p; j += 64) {
+            double nn = 0.0;
+            for (int l = l16; l < p; l += 16) nn = fma(Hc[j * p + l], Hc[j * p + l], nn);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o, 16);
+            if (l16 == 0) nrm[j] = nn;
+        }
+        __syncthreads();
+        for (int j = 0; j < p; j++) tr += nrm[j];
+        __syncthreads();
+    } else {
+        // sum the split-K partials with coalesced reads (fixed order per element), then symmetrise in shared memory
+        for (int e = tid; e < p * p; e += 1024) {
+            const int i = e % p, j = e / p;
+            double v = 0.0;
+            if (i < q && j < q)
+                for (int z = 0; z < splits; z++) v += H[(size_t)z * q * q + i + (size_t)q * j];
+            Hc[e] = v;
+            Vc[e] = (i == j) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        for (int e = tid; e < p * p; e += 1024) {
+            const int i = e % p, j = e / p;
+            if (i < j) {
+                const double v = 0.5 * (Hc[i + p * j] + Hc[j + p * i]);
+                Hc[i + p * j] = v;
+                Hc[j + p * i] = v;
+            }
+        }
+        __syncthreads();
+        for (int i = 0; i < p; i++) tr += Hc[i * p + i];
+    }
+    // rotation floor on gamma^2: columns of H J carry absolute noise eps*trace, columns of L J carry eps*sqrt(trace)
+    const double thr2 = LMODE ? (2.2e-16 * 2.2e-16) * tr : (8.9e-16 * tr) * (8.9e-16 * tr);
     const bool active = hw < hp;
     const bool warp_active = (tid >> 5) * 2 < hp;      // warps without a pair only take part in the barriers
     int sweep = 0;
@@ -273,13 +307,22 @@ sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* _
 #pragma unroll
                     for (int t = 0; t < NT; t++) {
                         if (FULL || (l16 + 16 * t < p)) {
-                            const double ya = va[16 * t], yb = vb[16 * t];
                             ha[16 * t] = c * xa[t] - sn * xb[t];
                             hb[16 * t] = sn * xa[t] + c * xb[t];
-                            va[16 * t] = c * ya - sn * yb;
-                            vb[16 * t] = sn * ya + c * yb;
+                            if (!LMODE) {
+                                const double ya = va[16 * t], yb = vb[16 * t];
+                                va[16 * t] = c * ya - sn * yb;
+                                vb[16 * t] = sn * ya + c * yb;
+                            }
                         }
                     }
+#ifdef MPST_KDEBUG
+                    if (l16 == 0) {
+                        atomicAdd(&dbg_rot, 1);
+                        if (g2 > 1e-16 * ab) atomicAdd(&dbg_big, 1);
+                        atomicMax(&dbg_max, (unsigned long long)__double_as_longlong(g2 / ab));
+                    }
+#endif
                     if (l16 == 0) {
                         // |h_a'|^2 = c^2 al - 2cs ga + s^2 be,  |h_b'|^2 = s^2 al + 2cs ga + c^2 be
                         const double cs2 = 2.0 * c * sn * ga, cc = c * c, ss = sn * sn;
@@ -294,6 +337,12 @@ sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* _
             b = (hw == 0) ? b + 1 : ((b + 1 == p - 1) ? 0 : b + 1);
             __syncthreads();
         }
+#ifdef MPST_KDEBUG
+        if (tid == 0) {
+            printf("[eig sweep %d] rotations %d big %d max cos %.3e\n", sweep, dbg_rot, dbg_big, sqrt(__longlong_as_double((long long)dbg_max)));
+            dbg_rot = 0; dbg_big = 0; dbg_max = 0ull;
+        }
+#endif
         // quadratic convergence: a sweep whose largest rotated cosine was <= 1e-8 leaves cosines at ~1e-16
         if (!any_rot || !any_big) break;
         __syncthreads();
@@ -303,40 +352,47 @@ sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* _
 #endif
     if (tid == 0 && sweep >= 60) atomicOr(status, 2);
     if (tid == 0) status[1] = sweep;
-    for (int e = tid; e < p * p; e += 1024) W[e] = Vc[e];
-    for (int j = hw; j < p; j += 64) {                 // lambda_j = || (H J)_j ||
+    if (!LMODE)
+        for (int e = tid; e < p * p; e += 1024) W[e] = Vc[e];
+    for (int j = hw; j < p; j += 64) {                 // lambda_j = || (H J)_j ||  resp.  || (L J)_j ||^2, w_j = (L J)_j / sigma_j
         double nn = 0.0;
         for (int l = l16; l < p; l += 16) nn += Hc[j * p + l] * Hc[j * p + l];
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o, 16);
-        if (l16 == 0) ev[j] = sqrt(nn);
+        if (LMODE) {
+            const double inv = nn > 0.0 ? rsqrt(nn) : 0.0;
+            for (int l = l16; l < p; l += 16) W[(size_t)j * p + l] = Hc[j * p + l] * inv;
+            if (l16 == 0) ev[j] = nn;
+        } else if (l16 == 0) ev[j] = sqrt(nn);
     }
 }
 
-template <int NT>
+template <int NT, bool LMODE>
 int launch_sym_eig_nt(int p, size_t smem, const double* H, int splits, int q, double* W, double* ev, int* status, cudaStream_t st) {
     if (p % 16 == 0) {
-        cudaError_t e = cudaFuncSetAttribute(sym_eig_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(sym_eig_kernel<NT, true, LMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        sym_eig_kernel<NT, true><<<1, 1024, smem, st>>>(H, splits, q, p, W, ev, status);
+        sym_eig_kernel<NT, true, LMODE><<<1, 1024, smem, st>>>(H, splits, q, p, W, ev, status);
     } else {
-        cudaError_t e = cudaFuncSetAttribute(sym_eig_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(sym_eig_kernel<NT, false, LMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        sym_eig_kernel<NT, false><<<1, 1024, smem, st>>>(H, splits, q, p, W, ev, status);
+        sym_eig_kernel<NT, false, LMODE><<<1, 1024, smem, st>>>(H, splits, q, p, W, ev, status);
     }
     return 0;
 }
 
+// LMODE = false: H = `splits` partial Gram matrices (q x q);  LMODE = true: H = lower Cholesky factor (p x p, q == p)
+template <bool LMODE>
 int launch_sym_eig(int p, size_t smem, const double* H, int splits, int q, double* W, double* ev, int* status, cudaStream_t st) {
     switch ((p + 15) / 16) {
-        case 1: return launch_sym_eig_nt<1>(p, smem, H, splits, q, W, ev, status, st);
-        case 2: return launch_sym_eig_nt<2>(p, smem, H, splits, q, W, ev, status, st);
-        case 3: return launch_sym_eig_nt<3>(p, smem, H, splits, q, W, ev, status, st);
-        case 4: return launch_sym_eig_nt<4>(p, smem, H, splits, q, W, ev, status, st);
-        case 5: return launch_sym_eig_nt<5>(p, smem, H, splits, q, W, ev, status, st);
-        case 6: return launch_sym_eig_nt<6>(p, smem, H, splits, q, W, ev, status, st);
-        case 7: return launch_sym_eig_nt<7>(p, smem, H, splits, q, W, ev, status, st);
-        default: return launch_sym_eig_nt<8>(p, smem, H, splits, q, W, ev, status, st);
+        case 1: return launch_sym_eig_nt<1, LMODE>(p, smem, H, splits, q, W, ev, status, st);
+        case 2: return launch_sym_eig_nt<2, LMODE>(p, smem, H, splits, q, W, ev, status, st);
+        case 3: return launch_sym_eig_nt<3, LMODE>(p, smem, H, splits, q, W, ev, status, st);
+        case 4: return launch_sym_eig_nt<4, LMODE>(p, smem, H, splits, q, W, ev, status, st);
+        case 5: return launch_sym_eig_nt<5, LMODE>(p, smem, H, splits, q, W, ev, status, st);
+        case 6: return launch_sym_eig_nt<6, LMODE>(p, smem, H, splits, q, W, ev, status, st);
+        case 7: return launch_sym_eig_nt<7, LMODE>(p, smem, H, splits, q, W, ev, status, st);
+        default: return launch_sym_eig_nt<8, LMODE>(p, smem, H, splits, q, W, ev, status, st);
     }
 }
 
@@ -462,7 +518,7 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         p = std::min((int)round_up(2 * k + (getenv("MPST_SVD_OVS") ? atoi(getenv("MPST_SVD_OVS")) : 0), 16), PMAX);
         if (p < k + 32 || n <= p || m < p) return MPST_OK;            // too little oversampling: full Jacobi
     }
-    const size_t need = (size_t)2 * n * p + (size_t)2 * m * p + (size_t)(MAXSPLIT + 3) * p * p + (size_t)n * k +
+    const size_t need = (size_t)2 * n * p + (size_t)2 * m * p + (size_t)(MAXSPLIT + 4) * p * p + (size_t)n * k +
                         (size_t)m * k + 4 * p + 64;
     TRY(ensure_buf(c, &c->sub, &c->subcap, need));
     double* Qa = c->sub;
@@ -473,7 +529,8 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     double* Ri = Gm + (size_t)MAXSPLIT * p * p;
     double* Wm = Ri + (size_t)p * p;
     double* Wk = Wm + (size_t)p * p;
-    double* T2 = Wk + (size_t)p * p;                                   // n x k
+    double* Lm = Wk + (size_t)p * p;                                   // Cholesky factor of the Ritz matrix
+    double* T2 = Lm + (size_t)p * p;                                   // n x k
     double* Uk = T2 + (size_t)n * k;                                   // m x k
     double* ev = Uk + (size_t)m * k;                                   // p, then Psorted p
     int* status = c->iscal + 8;
@@ -509,7 +566,7 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         int splits = 1;
         if (mode == 0) TRY(launch_dgemm_splitk(c, 1, 0, q, q, m, M, ldm, M, ldm, Gm, MAXSPLIT, &splits));   // M^T M
         else TRY(launch_dgemm_splitk(c, 0, 1, q, q, n, M, ldm, M, ldm, Gm, MAXSPLIT, &splits));            // M M^T
-        if (launch_sym_eig(p, eig_smem, Gm, splits, q, Wm, ev, status, c->stream)) CUDA_TRY(c, cudaGetLastError());
+        if (launch_sym_eig<false>(p, eig_smem, Gm, splits, q, Wm, ev, status, c->stream)) CUDA_TRY(c, cudaGetLastError());
         ritz_trunc_kernel<<<1, 256, 0, c->stream>>>(ev, p, q, trace_dev, chi_max, cutoff, c->perm, ev + p, c->iscal);
         gather_cols_kernel<<<(p * k + 255) / 256, 256, 0, c->stream>>>(Wm, p, c->perm, k, Wk);
         c->launches += 3;
@@ -541,7 +598,7 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     auto cholqr = [&](double* X, double* out, int rows) -> int {
         int splits = 1;
         TRY(launch_dgemm_splitk(c, 1, 0, p, p, rows, X, rows, X, rows, Gm, MAXSPLIT, &splits));
-        launch_chol_inv(p, Gm, splits, Ri, status, c->stream);
+        launch_chol_inv(p, Gm, splits, Ri, nullptr, status, c->stream);
         c->launches++;
         TRY(launch_dgemm(c, 0, 0, rows, p, p, X, rows, Ri, p, out, rows));
         return MPST_OK;
@@ -570,7 +627,10 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         int splits = 1;
         TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, Qa, n, Za, m));                // Z = M Q
         TRY(launch_dgemm_splitk(c, 1, 0, p, p, m, Za, m, Za, m, Gm, MAXSPLIT, &splits));   // H = Z^T Z
-        if (launch_sym_eig(p, eig_smem, Gm, splits, p, Wm, ev, status, c->stream)) CUDA_TRY(c, cudaGetLastError());
+        // H = L L^T (Cholesky in registers, breakdown -> status -> exact fallback), then Jacobi on the columns of L
+        launch_chol_inv(p, Gm, splits, Ri, Lm, status, c->stream);
+        if (launch_sym_eig<true>(p, eig_smem, Lm, 1, p, Wm, ev, status, c->stream)) CUDA_TRY(c, cudaGetLastError());
+        c->launches++;
         ritz_trunc_kernel<<<1, 256, 0, c->stream>>>(ev, p, n, trace_dev, chi_max, cutoff, c->perm, ev + p, c->iscal);
         gather_cols_kernel<<<(p * k + 255) / 256, 256, 0, c->stream>>>(Wm, p, c->perm, k, Wk);
         c->launches += 3;
