@@ -93,16 +93,42 @@ dgemm_kernel(const double* __restrict__ A, int64_t sai, int64_t sak, const doubl
         }
     }
 }
+
+// C[i + ldc*j] = sum_z parts[z][i + M*j]   (fixed order)
+__global__ void splitk_reduce_kernel(const double* __restrict__ parts, int splits, int M, int N, double* __restrict__ C,
+                                     int64_t ldc) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)M * N) return;
+    double v = 0.0;
+    for (int z = 0; z < splits; z++) v += parts[(size_t)z * M * N + e];
+    const int j = (int)(e / M), i = (int)(e - (int64_t)j * M);
+    C[i + ldc * j] = v;
+}
 }  // namespace
 
 // C = op(A) * op(B); ta/tb: 0 = as stored (column-major), 1 = transposed.
+// The subspace SVD's products are tiny next to the machine (tens of MFLOP) but long in K: when the output tiles
+// cover less than half of the SMs the K loop is split across CTAs and the partials are summed in a fixed order.
 int launch_dgemm(mpst_ctx* c, int ta, int tb, int M, int N, int K, const double* A, int64_t lda, const double* B,
                  int64_t ldb, double* C, int64_t ldc) {
     if (M <= 0 || N <= 0) return MPST_OK;
     const int64_t sai = ta ? lda : 1, sak = ta ? 1 : lda;
     const int64_t sbk = tb ? ldb : 1, sbj = tb ? 1 : ldb;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-    dgemm_kernel<<<grid, 256, 0, c->stream>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, (K + BK - 1) / BK, 0);
+    const int tiles = grid.x * grid.y, nk = (K + BK - 1) / BK;
+    int splits = std::min(c->sm_count / std::max(tiles, 1), nk / 4);
+    if (splits >= 2) {
+        const int kper = (nk + splits - 1) / splits;
+        splits = (nk + kper - 1) / kper;
+        if (ensure_buf(c, &c->gws, &c->gwscap, (size_t)splits * M * N) != MPST_OK) return MPST_E_CUDA;
+        grid.z = splits;
+        dgemm_kernel<<<grid, 256, 0, c->stream>>>(A, sai, sak, B, sbk, sbj, c->gws, M, M, N, K, kper, (int64_t)M * N);
+        splitk_reduce_kernel<<<(unsigned)(((int64_t)M * N + 255) / 256), 256, 0, c->stream>>>(c->gws, splits, M, N, C, ldc);
+        c->launches += 2;
+        CUDA_TRY(c, cudaGetLastError());
+        return MPST_OK;
+    }
+    dgemm_kernel<<<grid, 256, 0, c->stream>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, nk, 0);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
     return MPST_OK;

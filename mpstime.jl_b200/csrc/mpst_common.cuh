@@ -88,6 +88,8 @@ struct mpst_ctx {
     int* perm = nullptr;        // [npad]
     double* sub = nullptr;      // subspace-SVD workspace
     size_t subcap = 0;
+    double* gws = nullptr;      // split-K partial products of the small GEMMs
+    size_t gwscap = 0;
     int* flags = nullptr;       // dataflow counters of the fused Jacobi sweep
     size_t flagcap = 0;
     int* iscal = nullptr;       // device ints [16]
