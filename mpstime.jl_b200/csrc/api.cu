@@ -22,6 +22,9 @@ int launch_fill(mpst_ctx* c, double* v, int64_t n, double val);
 int launch_argmax(mpst_ctx* c, const double* yhat, int64_t Npad, int64_t n, int C, double* out_yhat, int64_t* out_arg);
 int launch_bond_grad(mpst_ctx* c, const double* xl, const double* xr, const double* L, const double* R, int d,
                      int chi_l, int chi_r, const int64_t* cls_begin, const int64_t* cls_end, int ncls, double* G);
+int launch_bond_grad_kr(mpst_ctx* c, const double* xl, const double* xr, const double* L, const double* R, int d,
+                        int chi_l, int chi_r, const int64_t* cls_begin, const int64_t* cls_end, int ncls, double* G,
+                        bool* handled);
 int svd_split_device(mpst_ctx* c, const double* B, int Dl, int Dr, int C, int going_left, int chi_max,
                      double cutoff, const double* norm2_dev, double* label_core, double* ortho_core,
                      int* chi_new, double* sigma_host, int* sweeps_out);
@@ -517,7 +520,9 @@ static int loss_grad_device(mpst_ctx* c, const double* phl, const double* phr, c
             cb[cls] = loss_kind == MPST_LOSS_KLD ? c->class_off[cls] : 0;
             ce[cls] = loss_kind == MPST_LOSS_KLD ? c->class_off[cls + 1] : c->N;
         }
-        TRY(launch_bond_grad(c, phl, phr, L, R, d, chi_l, chi_r, cb.data(), ce.data(), C, G));
+        bool kr_done = false;
+        TRY(launch_bond_grad_kr(c, phl, phr, L, R, d, chi_l, chi_r, cb.data(), ce.data(), C, G, &kr_done));
+        if (!kr_done) TRY(launch_bond_grad(c, phl, phr, L, R, d, chi_l, chi_r, cb.data(), ce.data(), C, G));
     }
     (void)train_sep;
     return MPST_OK;
