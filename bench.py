@@ -34,6 +34,10 @@ WORKLOAD = dict(name="trendy_sine_N100k_T100_d12_chi40", N=100_000, T=100, d=12,
                 periods=((12.0, 15.0), (16.0, 19.0)), slopes=(-3.0, 0.0, 3.0), sigma=0.1, chi_init=4)
 FP64_PEAK_TFLOPS = 35.4      # cuBLAS DGEMM measured on this pool (profiles/r01_dgemm_calib.txt); MEASURED_PEAKS.json has no FP64 entry
 FP64_PEAK_NOTE = "fallback: same-pool cuBLAS DGEMM 8192^3 = 35.4 TFLOP/s (DMMA issue peak 37.1); MEASURED_PEAKS.json carries no FP64 figure"
+# dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch of the gradient kernel at config B shapes
+# (ncu --set full, profiles/r01_bond_grad_kr_ncu_full.txt); algorithmic bytes are 84 MB, the kernel is tensor bound
+NCU_TRAFFIC_BYTES = 258.4e6
+NCU_TRAFFIC_NOTE = "profiles/r01_bond_grad_kr_ncu_full.txt (ncu --set full, launch 60 of a config-B sweep): 250.4 MB read + 8.0 MB written"
 
 
 def trendy_sine(T, n, period, slopes, sigma, rng):
@@ -336,8 +340,9 @@ def main():
         return
     gk_ms, gk_n, gk_fl = prof["grad_kernel"]
     achieved = gk_fl / (gk_ms * 1e-3) / 1e12 if gk_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "bond_grad_kernel", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
-                "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None, "peak_source": FP64_PEAK_NOTE,
+    roofline = {"bound": "tensor", "kernel": "bond_grad_kr_kernel", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
+                "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": NCU_TRAFFIC_BYTES,
+                "traffic_source": NCU_TRAFFIC_NOTE, "peak_source": FP64_PEAK_NOTE,
                 "launches": gk_n, "avg_launch_ms": gk_ms / max(gk_n, 1),
                 "algorithmic_flops_per_launch": gk_fl / max(gk_n, 1)}
     breakdown = {k: {"ms": round(v[0], 3), "n": v[1]} for k, v in prof.items() if v[1]}
