@@ -121,15 +121,28 @@ static int core_orient(mpst_ctx* c, int site, int want) {
 static size_t slot_stride(const mpst_ctx* c) { return (size_t)c->Npad * c->chi_max; }
 static double* slot_ptr(mpst_ctx* c, int site) { return c->env + (size_t)site * slot_stride(c); }
 
-static void free_training(mpst_ctx* c) {
-    auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
-    fr(c->X); fr(c->PHI); fr(c->phi_l); fr(c->phi_r); fr(c->env); fr(c->ones); fr(c->yhat); fr(c->w);
-    for (auto& k : c->cores) if (k.dev) cudaFree(k.dev);
-    c->cores.clear();
+// Logical reset between models / data sets.  The big device buffers are kept (grow-only, see reserve()) so that
+// re-loading a data set of the same shape costs copies only, not cudaFree + cudaMalloc of gigabytes.
+static void free_training(mpst_ctx* c, bool release = false) {
+    if (release) {
+        auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
+        fr(c->X); fr(c->PHI); fr(c->phi_l); fr(c->phi_r); fr(c->env); fr(c->ones); fr(c->yhat); fr(c->w);
+        c->cap_X = c->cap_PHI = c->cap_phi = c->cap_env = c->cap_ones = c->cap_yw = 0;
+        for (auto& k : c->cores) if (k.dev) cudaFree(k.dev);
+        c->cores.clear();
+    }
     c->env_chi.clear();
     c->N = c->Npad = 0;
     c->T = 0;
     c->meta_key = 0;
+}
+
+static int reserve(mpst_ctx* c, double*& p, size_t& cap, size_t need) {
+    if (p && need <= cap) return MPST_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    CUDA_TRY(c, cudaMalloc(&p, need * sizeof(double)));
+    cap = need;
+    return MPST_OK;
 }
 
 // ---- NCCL through dlopen (no link-time dependency; prefers the copy already in the process) ---
@@ -209,7 +222,7 @@ int mpst_destroy(mpst_ctx* c) {
     cudaStreamSynchronize(c->stream);
     prof_drain(c);
     for (auto e : c->evpool) cudaEventDestroy(e);
-    free_training(c);
+    free_training(c, true);
     auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(c->B); fr(c->G); fr(c->Z); fr(c->part); fr(c->red); fr(c->scal); fr(c->S); fr(c->gpart); fr(c->wbuf);
     fr(c->colnorm); fr(c->tmp); fr(c->meta); fr(c->sub); fr(c->gws);
@@ -282,7 +295,12 @@ static int model_reset(mpst_ctx* c, int T, int C, int d, int chi_max) {
     free_training(c);
     c->T = T; c->C = C; c->d = d; c->chi_max = chi_max;
     c->env_chi.assign(T, 0);
-    c->cores.assign(T, Core());
+    if ((int)c->cores.size() != T) {
+        for (auto& k : c->cores) if (k.dev) cudaFree(k.dev);
+        c->cores.assign(T, Core());
+    } else {
+        for (auto& k : c->cores) { k.chi_l = k.chi_r = 0; k.has_label = 0; k.orient = ORIENT_LEFT; }   // keep dev/cap
+    }
     return MPST_OK;
 }
 
@@ -300,16 +318,22 @@ static int train_common(mpst_ctx* c, int64_t N, int T, const int64_t* class_coun
     c->counts_global.assign(counts_global ? counts_global : class_counts, (counts_global ? counts_global : class_counts) + C);
     c->class_off.assign(C + 1, 0);
     for (int k = 0; k < C; k++) c->class_off[k + 1] = c->class_off[k] + class_counts[k];
-    CUDA_TRY(c, cudaMalloc(&c->phi_l, sizeof(double) * c->Npad * d));
-    CUDA_TRY(c, cudaMalloc(&c->phi_r, sizeof(double) * c->Npad * d));
+    {
+        size_t cap_r = c->cap_phi;
+        TRY(reserve(c, c->phi_l, c->cap_phi, (size_t)c->Npad * d));
+        TRY(reserve(c, c->phi_r, cap_r, (size_t)c->Npad * d));
+    }
     CUDA_TRY(c, cudaMemsetAsync(c->phi_l, 0, sizeof(double) * c->Npad * d, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->phi_r, 0, sizeof(double) * c->Npad * d, c->stream));
-    CUDA_TRY(c, cudaMalloc(&c->env, sizeof(double) * slot_stride(c) * T));
+    TRY(reserve(c, c->env, c->cap_env, (size_t)slot_stride(c) * T));
     CUDA_TRY(c, cudaMemsetAsync(c->env, 0, sizeof(double) * slot_stride(c) * T, c->stream));
-    CUDA_TRY(c, cudaMalloc(&c->ones, sizeof(double) * c->Npad));
+    TRY(reserve(c, c->ones, c->cap_ones, (size_t)c->Npad));
     TRY(launch_fill(c, c->ones, c->Npad, 1.0));
-    CUDA_TRY(c, cudaMalloc(&c->yhat, sizeof(double) * c->Npad * C));
-    CUDA_TRY(c, cudaMalloc(&c->w, sizeof(double) * c->Npad * C));
+    {
+        size_t cap_w = c->cap_yw;
+        TRY(reserve(c, c->yhat, c->cap_yw, (size_t)c->Npad * C));
+        TRY(reserve(c, c->w, cap_w, (size_t)c->Npad * C));
+    }
     CUDA_TRY(c, cudaMemsetAsync(c->yhat, 0, sizeof(double) * c->Npad * C, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->w, 0, sizeof(double) * c->Npad * C, c->stream));
     return MPST_OK;
@@ -334,7 +358,8 @@ int mpst_train_load_x(mpst_ctx* c, const double* X, int64_t N, int T, const int6
     TRY(train_common(c, N, T, class_counts, C, d, chi_max, n_global, counts_global));
     c->basis = basis_id;
     c->have_phi = false;
-    CUDA_TRY(c, cudaMalloc(&c->X, sizeof(double) * c->Npad * T));
+    if (c->PHI) { cudaFree(c->PHI); c->PHI = nullptr; c->cap_PHI = 0; }
+    TRY(reserve(c, c->X, c->cap_X, (size_t)c->Npad * T));
     CUDA_TRY(c, cudaMemsetAsync(c->X, 0, sizeof(double) * c->Npad * T, c->stream));
     // host: T x N column-major == row-major [N][T]; device: site-major [T][Npad]
     const int64_t chunk = std::max<int64_t>(1, (int64_t)(64 << 20) / (8 * (int64_t)T));
@@ -354,7 +379,8 @@ int mpst_train_load_phi(mpst_ctx* c, const double* phi, int64_t N, int T, const 
     TRY(train_common(c, N, T, class_counts, C, d, chi_max, n_global, counts_global));
     c->basis = MPST_BASIS_PRECOMPUTED;
     c->have_phi = true;
-    CUDA_TRY(c, cudaMalloc(&c->PHI, sizeof(double) * c->Npad * d * T));
+    if (c->X) { cudaFree(c->X); c->X = nullptr; c->cap_X = 0; }
+    TRY(reserve(c, c->PHI, c->cap_PHI, (size_t)c->Npad * d * T));
     CUDA_TRY(c, cudaMemsetAsync(c->PHI, 0, sizeof(double) * c->Npad * d * T, c->stream));
     // host [N][T][d] -> device [T][Npad][d]: one strided 2-D copy per site
     for (int j = 0; j < T; j++)

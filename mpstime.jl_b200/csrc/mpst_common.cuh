@@ -89,6 +89,8 @@ struct mpst_ctx {
     double* sub = nullptr;      // subspace-SVD workspace
     size_t subcap = 0;
     double* gws = nullptr;      // split-K partial products of the small GEMMs
+    // capacities (doubles) of the training buffers: a re-load with the same or a smaller shape reuses them
+    size_t cap_X = 0, cap_PHI = 0, cap_phi = 0, cap_env = 0, cap_ones = 0, cap_yw = 0;
     size_t gwscap = 0;
     int* flags = nullptr;       // dataflow counters of the fused Jacobi sweep
     size_t flagcap = 0;
