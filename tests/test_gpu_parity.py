@@ -64,6 +64,10 @@ SHAPES = [  # N, d, chi_l, chi_r, C, counts
     (1500, 16, 64, 64, 2, [1499, 1]),     # north-star bond shape, extreme imbalance
     (513, 10, 20, 20, 2, None),           # BASELINE config A shape
     (700, 24, 16, 16, 2, None),           # micro-sweep corner d=24
+    (400, 12, 10, 14, 2, None),           # register-operand kernel, partial 8-wide link blocks on both sides
+    (333, 6, 8, 22, 3, [300, 2, 31]),     # one site group per side, ragged classes, chunk-straddling class edges
+    (200, 8, 12, 30, 2, None),            # d % 4 variant (2 link blocks x 4 sites per warp)
+    (50, 18, 8, 8, 2, [49, 1]),           # fewer samples than one stream-K range per SM
 ]
 
 
