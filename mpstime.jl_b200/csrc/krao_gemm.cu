@@ -94,9 +94,17 @@ krao_gemm_kernel(const double* __restrict__ x, const double* __restrict__ E,
         for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
     const int fr = lane >> 2, fc = lane & 3;
+    // Warps 0-3 stage the next chunk first and then run their DMMAs, warps 4-7 the other way round: every SM
+    // sub-partition hosts one warp of each kind, so its tensor pipe has DMMAs queued while the other warp is on the
+    // load/multiply/store work of the staging.
+    const bool stage_first = (warp & 4) == 0;
     for (int kc = 0; kc < nk; kc++) {
         const int cur = kc & 1;
         if (kc + 1 < nk) load_w(kc + 1);
+        if (stage_first && kc + 1 < nk) {
+            build_p(kc + 1, cur ^ 1);
+            store_w(cur ^ 1);
+        }
         const double* Pc = Ps + cur * TM * LDP + (wm * (TM / WM) + fr) * LDP + fc;
         const double* Wc = Ws + cur * TN * LDP + (wn * (TN / WN) + fr) * LDP + fc;
 #pragma unroll
@@ -111,7 +119,7 @@ krao_gemm_kernel(const double* __restrict__ x, const double* __restrict__ E,
 #pragma unroll
                 for (int ni = 0; ni < NI; ni++) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
-        if (kc + 1 < nk) {
+        if (!stage_first && kc + 1 < nk) {
             build_p(kc + 1, cur ^ 1);
             store_w(cur ^ 1);
         }

@@ -596,9 +596,10 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     // ---- subspace iteration ----
     // X (rows x p, ld = rows) -> orthonormal columns in `out`
     auto cholqr = [&](double* X, double* out, int rows) -> int {
-        int splits = 1;
-        TRY(launch_dgemm_splitk(c, 1, 0, p, p, rows, X, rows, X, rows, Gm, MAXSPLIT, &splits));
-        launch_chol_inv(p, Gm, splits, Ri, nullptr, status, c->stream);
+        // Gram matrix through the auto split-K GEMM (partials summed by a wide reduce kernel): the single-CTA
+        // Cholesky then reads one p x p matrix instead of ~15 partials (its load phase was as long as its pivot loop)
+        TRY(launch_dgemm(c, 1, 0, p, p, rows, X, rows, X, rows, Gm, p));
+        launch_chol_inv(p, Gm, 1, Ri, nullptr, status, c->stream);
         c->launches++;
         TRY(launch_dgemm(c, 0, 0, rows, p, p, X, rows, Ri, p, out, rows));
         return MPST_OK;
@@ -626,7 +627,8 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         // Rayleigh-Ritz
         int splits = 1;
         TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, Qa, n, Za, m));                // Z = M Q
-        TRY(launch_dgemm_splitk(c, 1, 0, p, p, m, Za, m, Za, m, Gm, MAXSPLIT, &splits));   // H = Z^T Z
+        TRY(launch_dgemm(c, 1, 0, p, p, m, Za, m, Za, m, Gm, p));                 // H = Z^T Z
+        splits = 1;
         // H = L L^T (Cholesky in registers, breakdown -> status -> exact fallback), then Jacobi on the columns of L
         launch_chol_inv(p, Gm, splits, Ri, Lm, status, c->stream);
         if (launch_sym_eig<true>(p, eig_smem, Lm, 1, p, Wm, ev, status, c->stream)) CUDA_TRY(c, cudaGetLastError());
