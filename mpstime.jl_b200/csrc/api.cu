@@ -295,6 +295,8 @@ static int model_reset(mpst_ctx* c, int T, int C, int d, int chi_max) {
     free_training(c);
     c->T = T; c->C = C; c->d = d; c->chi_max = chi_max;
     c->env_chi.assign(T, 0);
+    c->svd_its.clear();
+    c->svd_floor.clear();
     if ((int)c->cores.size() != T) {
         for (auto& k : c->cores) if (k.dev) cudaFree(k.dev);
         c->cores.assign(T, Core());
@@ -657,8 +659,12 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         const size_t cap = (size_t)d * c->chi_max * c->chi_max * C;
         TRY(core_reserve(c, klabel, cap));
         TRY(core_reserve(c, kortho, cap));
-        TRY(svd_split_device(c, c->B, Dl, Dr, C, going_left, o->chi_max, o->cutoff, norm2_dev, klabel.dev, kortho.dev,
-                             &chi_new, nullptr, nullptr));
+        if ((int)c->svd_its.size() != c->T) { c->svd_its.assign(c->T, 0); c->svd_floor.assign(c->T, 0); }
+        c->svd_slot = l;
+        const int rc_svd = svd_split_device(c, c->B, Dl, Dr, C, going_left, o->chi_max, o->cutoff, norm2_dev, klabel.dev,
+                                            kortho.dev, &chi_new, nullptr, nullptr);
+        c->svd_slot = -1;
+        TRY(rc_svd);
     }
     if (going_left) {       // W[l] <- U*S with the label (LEFT), W[r] <- V (RIGHT)   (:161-176)
         kl.chi_r = chi_new; kl.has_label = 1; kl.orient = ORIENT_LEFT;

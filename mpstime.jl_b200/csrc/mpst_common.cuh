@@ -89,6 +89,10 @@ struct mpst_ctx {
     double* sub = nullptr;      // subspace-SVD workspace
     size_t subcap = 0;
     double* gws = nullptr;      // split-K partial products of the small GEMMs
+    // per-bond subspace-iteration count learned during training (svd_subspace.cu): svd_slot = bond being split
+    // (-1: none), svd_its[b] = iterations to start with, svd_floor[b] = smallest count that has not failed yet
+    int svd_slot = -1;
+    std::vector<int> svd_its, svd_floor;
     // capacities (doubles) of the training buffers: a re-load with the same or a smaller shape reuses them
     size_t cap_X = 0, cap_PHI = 0, cap_phi = 0, cap_env = 0, cap_ones = 0, cap_yw = 0;
     size_t gwscap = 0;

@@ -614,7 +614,13 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     const int max_rounds = 3;
     int iters_done = 0;
     for (int round = 0; round < max_rounds; round++) {
-        const int niter = round == 0 ? (getenv("MPST_SVD_IT") ? atoi(getenv("MPST_SVD_IT")) : (p >= 2 * k ? 5 : 7)) : 3;
+        // iterations of the first round: 5 unless this bond's previous visits showed that fewer reach the residual
+        // bound (trained spectra change slowly from sweep to sweep); a visit that needs a second round raises the
+        // bond's floor for good, so every level is tried at most once per bond
+        const int slot = (c->svd_slot >= 0 && c->svd_slot < (int)c->svd_its.size()) ? c->svd_slot : -1;
+        int first = getenv("MPST_SVD_IT") ? atoi(getenv("MPST_SVD_IT")) : (p >= 2 * k ? 5 : 7);
+        if (slot >= 0 && c->svd_its[slot] > 0 && !getenv("MPST_SVD_IT")) first = c->svd_its[slot];
+        const int niter = round == 0 ? first : 3;
         for (int it = 0; it < niter; it++) {
             TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, Qa, n, Za, m));            // Z = M Q
             TRY(cholqr(Za, Zb, m));
@@ -652,6 +658,16 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         if (c->hiscal[8] != 0 || !(res == res)) {
             if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d breakdown status=%d -> full Jacobi\n", m, n, c->hiscal[8]);
             return MPST_OK;
+        }
+        if (slot >= 0) {
+            if (round == 0 && res <= 5e-14) {
+                // passed at `first`: try one fewer next time if that level has not failed before and the margin is there
+                if (res <= 1.5e-14 && first - 1 >= std::max(3, c->svd_floor[slot])) c->svd_its[slot] = first - 1;
+                else c->svd_its[slot] = first;
+            } else if (round == 0) {
+                c->svd_floor[slot] = first + 1;
+                c->svd_its[slot] = first + 1;
+            }
         }
         if (res <= 5e-14) return finish("subspace", iters_done, res);
         if (res > (round == 0 ? 1e-5 : 1e-10)) {                                   // spectrum too flat: full Jacobi
