@@ -100,6 +100,20 @@ static int core_reserve(mpst_ctx* c, Core& k, size_t need) {
     return MPST_OK;
 }
 
+static void mark_core(mpst_ctx* c, int j) { c->core_ver[j] = ++c->gen; }
+static void mark_env(mpst_ctx* c, int j, int dir) {
+    const int src = dir == 1 ? j - 1 : j + 1;
+    c->env_dir[j] = dir;
+    c->env_ver[j] = ++c->gen;
+    c->env_core_ver[j] = c->core_ver[j];
+    c->env_src_ver[j] = (src >= 0 && src < c->T) ? c->env_ver[src] : 0;
+}
+static bool env_fresh(const mpst_ctx* c, int j, int dir) {
+    const int src = dir == 1 ? j - 1 : j + 1;
+    return c->env_chi[j] > 0 && c->env_dir[j] == dir && c->env_core_ver[j] == c->core_ver[j] &&
+           c->env_src_ver[j] == ((src >= 0 && src < c->T) ? c->env_ver[src] : 0);
+}
+
 static int core_orient(mpst_ctx* c, int site, int want) {
     Core& k = c->cores[site];
     if (k.orient == want) return MPST_OK;
@@ -295,6 +309,8 @@ static int model_reset(mpst_ctx* c, int T, int C, int d, int chi_max) {
     free_training(c);
     c->T = T; c->C = C; c->d = d; c->chi_max = chi_max;
     c->env_chi.assign(T, 0);
+    c->core_ver.assign(T, 0); c->env_ver.assign(T, 0); c->env_core_ver.assign(T, 0); c->env_src_ver.assign(T, 0);
+    c->env_dir.assign(T, 0);
     c->svd_its.clear();
     c->svd_floor.clear();
     if ((int)c->cores.size() != T) {
@@ -403,6 +419,7 @@ int mpst_set_core(mpst_ctx* c, int site, const double* data, int chi_l, int chi_
     const size_t cap = (size_t)d * c->chi_max * c->chi_max * c->C;     // room for any later update
     TRY(core_reserve(c, k, std::max(cap, n)));
     k.chi_l = chi_l; k.chi_r = chi_r; k.has_label = has_label ? 1 : 0; k.orient = ORIENT_LEFT;
+    mark_core(c, site);
     TRY(ensure_buf(c, &c->tmp, &c->tmpcap, n));
     CUDA_TRY(c, cudaMemcpyAsync(c->tmp, data, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     // wire: a + chi_l*(s + d*(b + chi_r*c))  ->  LEFT: s + d*(a + chi_l*b) + d*chi_l*chi_r*c
@@ -465,6 +482,7 @@ int mpst_build_env(mpst_ctx* c, int going_left) {
             ProfScope ps(c, MPST_T_ENV);
             TRY(launch_krao_gemm(c, ph, E, k.dev, slot_ptr(c, j), c->N, d, k.chi_l, k.chi_r, (int64_t)d * k.chi_l, k.chi_r));
             c->env_chi[j] = k.chi_r;
+            mark_env(c, j, 1);
         }
     } else {
         for (int j = T - 1; j > pos; j--) {
@@ -476,6 +494,7 @@ int mpst_build_env(mpst_ctx* c, int going_left) {
             ProfScope ps(c, MPST_T_ENV);
             TRY(launch_krao_gemm(c, ph, E, k.dev, slot_ptr(c, j), c->N, d, k.chi_r, k.chi_l, (int64_t)d * k.chi_r, k.chi_l));
             c->env_chi[j] = k.chi_l;
+            mark_env(c, j, 2);
         }
     }
     return MPST_OK;
@@ -488,7 +507,7 @@ int mpst_build_env(mpst_ctx* c, int going_left) {
 static int loss_grad_device(mpst_ctx* c, const double* phl, const double* phr, const double* L, const double* R,
                             int chi_l, int chi_r, const double* B, double* G, int loss_kind, int train_sep,
                             double* loss_dev, int64_t* coff_dev, double* denom_dev, const Core* fac_l = nullptr,
-                            const Core* fac_r = nullptr) {
+                            const Core* fac_r = nullptr, const double* cached_unlab = nullptr) {
     const int d = c->d, C = c->C;
     const int Dl = d * chi_l, Dr = d * chi_r;
     const size_t D = (size_t)Dl * Dr;
@@ -504,7 +523,8 @@ static int loss_grad_device(mpst_ctx* c, const double* phl, const double* phr, c
             TRY(ensure_buf(c, &c->Z, &c->Zcap, (size_t)c->Npad * chi_m * (nbuf + 1)));
             double* Ab = c->Z;                                               // unlabelled side
             double* Lb = c->Z + (size_t)c->Npad * chi_m;                     // labelled side, nbuf buffers
-            if (lab_l) TRY(launch_krao_gemm_rows(c, phr, R, fac_r->dev, Ab, 0, c->N, d, chi_r, chi_m, Dr, chi_m));
+            if (cached_unlab) Ab = const_cast<double*>(cached_unlab);       // [Npad][chi_m], read only
+            else if (lab_l) TRY(launch_krao_gemm_rows(c, phr, R, fac_r->dev, Ab, 0, c->N, d, chi_r, chi_m, Dr, chi_m));
             else TRY(launch_krao_gemm_rows(c, phl, L, fac_l->dev, Ab, 0, c->N, d, chi_l, chi_m, Dl, chi_m));
             for (int cls = 0; cls < C; cls++) {
                 const int64_t b0 = loss_kind == MPST_LOSS_KLD ? c->class_off[cls] : 0;
@@ -627,8 +647,15 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
             TRY(core_orient(c, l, ORIENT_LEFT));
             TRY(core_orient(c, r, ORIENT_RIGHT));
         }
+        // The unlabelled forward factor P W_l (resp. Q W_r) is the environment of that site; when the slot still holds
+        // it -- computed from this very core and neighbour slot by the previous sweep direction -- the GEMM is skipped.
+        const double* cached = nullptr;
+        if (factored && !getenv("MPST_NO_ENV_REUSE")) {
+            const int u = kl.has_label ? r : l, dir = kl.has_label ? 2 : 1;
+            if (env_fresh(c, u, dir) && c->env_chi[u] == chi_m) cached = slot_ptr(c, u);
+        }
         TRY(loss_grad_device(c, phl, phr, L, R, chi_l, chi_r, c->B, c->G, o->loss_kind, o->train_sep, s_loss, coff_dev, denom_dev,
-                             factored ? &kl : nullptr, factored ? &kr : nullptr));
+                             factored ? &kl : nullptr, factored ? &kr : nullptr, cached));
         TRY(allreduce_sum(c, c->G, D * C + 1));
         ProfScope ps(c, MPST_T_UPDATE);
         TRY(launch_sumsq(c, c->G, D * C, s_gn2));
@@ -665,6 +692,8 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
                                             kortho.dev, &chi_new, nullptr, nullptr);
         c->svd_slot = -1;
         TRY(rc_svd);
+        mark_core(c, l);
+        mark_core(c, r);
     }
     if (going_left) {       // W[l] <- U*S with the label (LEFT), W[r] <- V (RIGHT)   (:161-176)
         kl.chi_r = chi_new; kl.has_label = 1; kl.orient = ORIENT_LEFT;
@@ -673,6 +702,7 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         TRY(launch_krao_gemm(c, phr, R, kr.dev, slot_ptr(c, r), c->N, d, chi_r, chi_new, Dr, chi_new));
         c->prof_work[MPST_T_ENV] += 2.0 * (double)c->N * Dr * chi_new;
         c->env_chi[r] = chi_new;
+        mark_env(c, r, 2);
     } else {                // W[l] <- U (LEFT), W[r] <- V*S with the label (RIGHT)   (:177-196)
         kl.chi_r = chi_new; kl.has_label = 0; kl.orient = ORIENT_LEFT;
         kr.chi_l = chi_new; kr.has_label = 1; kr.orient = ORIENT_RIGHT;
@@ -680,6 +710,7 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         TRY(launch_krao_gemm(c, phl, L, kl.dev, slot_ptr(c, l), c->N, d, chi_l, chi_new, Dl, chi_new));
         c->prof_work[MPST_T_ENV] += 2.0 * (double)c->N * Dl * chi_new;
         c->env_chi[l] = chi_new;
+        mark_env(c, l, 1);
     }
     if (chi_new_out) *chi_new_out = chi_new;
     return MPST_OK;
@@ -719,6 +750,7 @@ int mpst_sweep(mpst_ctx* c, const mpst_train_opts* o, int nsweeps, double* per_b
         for (int j = 0; j < T; j++) {
             Core& q = c->cores[j];
             TRY(launch_scale_const(c, q.dev, (size_t)c->d * q.chi_l * q.chi_r * (q.has_label ? c->C : 1), 1.0 / z));
+            mark_core(c, j);
         }
         // environments no longer match the rescaled cores
         std::fill(c->env_chi.begin(), c->env_chi.end(), 0);

@@ -91,6 +91,11 @@ struct mpst_ctx {
     double* gws = nullptr;      // split-K partial products of the small GEMMs
     // per-bond subspace-iteration count learned during training (svd_subspace.cu): svd_slot = bond being split
     // (-1: none), svd_its[b] = iterations to start with, svd_floor[b] = smallest count that has not failed yet
+    // provenance of the environment slots: slot j is reusable as the unlabelled forward factor of a bond when it
+    // was computed (dir 1 = LE, 2 = RE) from the current core j and the current neighbouring slot
+    uint64_t gen = 1;
+    std::vector<uint64_t> core_ver, env_ver, env_core_ver, env_src_ver;
+    std::vector<int> env_dir;
     int svd_slot = -1;
     std::vector<int> svd_its, svd_floor;
     // capacities (doubles) of the training buffers: a re-load with the same or a smaller shape reuses them
