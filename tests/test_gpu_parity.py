@@ -252,6 +252,39 @@ def test_free_running_sweep_matches_oracle(ctx, oracle, pkg):
     assert np.array_equal(np.argmax(yd * yd, 1), np.argmax(yr * yr, 1))
 
 
+def test_cached_environment_reuse_is_bit_exact(ctx, oracle, pkg, monkeypatch):
+    """The sweep takes the unlabelled forward factor from the environment slot of that site when the slot's provenance
+    (core version, neighbour slot version, direction) says it is still current.  Same kernel, same operands: the whole
+    trajectory must be bit-identical to recomputing the factor at every bond (MPST_NO_ENV_REUSE)."""
+    N, T, d, C = 300, 7, 6, 2
+    Xs, phi, ys, counts, cores = _problem(oracle, N, T, d, C)
+    out = []
+    for no_reuse in (False, True):
+        if no_reuse:
+            monkeypatch.setenv("MPST_NO_ENV_REUSE", "1")
+        ctx.train_load_x(Xs, counts, d, 12)
+        ctx.set_cores(cores)
+        lo, gn, chi = ctx.sweep(pkg.make_opts(chi_max=12, eta=0.05), 2)
+        out.append((lo, gn, chi, ctx.get_cores()))
+    (l0, g0, c0, k0), (l1, g1, c1, k1) = out
+    assert np.array_equal(l0, l1) and np.array_equal(g0, g1) and np.array_equal(c0, c1)
+    assert all(np.array_equal(a, b) for a, b in zip(k0, k1))
+    # a core replaced from the host invalidates the slot: the next bond step must not use the stale factor
+    ctx.train_load_x(Xs, counts, d, 12)
+    ctx.set_cores(cores)
+    ctx.build_env(True)
+    l_a, g_a, _ = ctx.bond_step(T - 2, True, pkg.make_opts(chi_max=12, eta=0.05))
+    ctx.set_cores(cores)
+    ctx.set_core(T - 2, 0.5 * cores[T - 2])                      # same shape, different values, environments untouched
+    l_b, g_b, _ = ctx.bond_step(T - 2, True, pkg.make_opts(chi_max=12, eta=0.05))
+    cs = [c.copy() for c in cores]
+    cs[T - 2] = 0.5 * cores[T - 2]
+    assert l_b != l_a
+    rec = []
+    oracle.fit_sweeps(cs, phi, counts, nsweeps=1, chi_max=12, eta=0.05, record=rec, max_bonds=1)
+    assert abs(l_b - rec[0]["loss"]) <= 1e-9 * abs(rec[0]["loss"])
+
+
 def test_phi_mode_equals_x_mode(ctx, oracle, pkg):
     """precomputed-phi entry (custom / data-driven bases) gives the same sweep as the on-device encoder."""
     Xs, phi, ys, counts, cores = _problem(oracle, 150, 6, 3)
