@@ -9,6 +9,8 @@
 // with two 1-D bulk-TMA copies on an mbarrier; W chunks are register-prefetched one chunk ahead.
 // Shared-memory operand pitches are == 4 (mod 16) doubles so every DMMA fragment load is
 // bank-conflict free.
+#include <algorithm>
+#include <cstdlib>
 #include "mpst_common.cuh"
 #include "dmma.cuh"
 
@@ -139,6 +141,104 @@ krao_gemm_kernel(const double* __restrict__ x, const double* __restrict__ E,
     }
 }
 
+// ---- register-operand variant for narrow outputs (environment update, unlabelled forward factor) ------------
+// The whole weight matrix W (K x n_out, K = d*chi) is resident in shared memory for the lifetime of a persistent
+// CTA (one per SM; columns arrive by bulk TMA with a pitch == 4 (mod 16), conflict free); every WARP owns 16 samples
+// at a time: it stages their x / E rows in its private shared-memory region, forms the Khatri-Rao A fragments in
+// registers (2 loads + 1 multiply each, reused by all n blocks) and streams through the K dimension without any
+// block barrier.  Work units (16 samples) are dealt round-robin to all warps of the grid.
+__host__ __device__ inline int kr_pitch4(int n) { return ((n + 11) / 16) * 16 + 4; }
+
+template <int NI>
+__global__ void __launch_bounds__(256, 1)
+krao_reg_kernel(const double* __restrict__ x, const double* __restrict__ E, const double* __restrict__ W,
+                double* __restrict__ out, int64_t row_begin, int64_t row_end, int d, int chi, int n_out, int64_t ldw,
+                int64_t ldo) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smraw);
+    double* Ws = reinterpret_cast<double*>(smraw + 16);
+    const int K = d * chi;
+    const int ldws = kr_pitch4(K), ldx = kr_pitch4(d), lde = kr_pitch4(chi);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* xs = Ws + (size_t)(8 * NI) * ldws + (size_t)warp * 16 * (ldx + lde);   // this warp's 16 x ldx | 16 x lde
+    double* es = xs + 16 * ldx;
+    const int fr = lane >> 2, fc = lane & 3;
+
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)((size_t)n_out * K * sizeof(double)));
+        __syncwarp();
+        for (int n = lane; n < n_out; n += 32) bulk_g2s(Ws + (size_t)n * ldws, W + ldw * (int64_t)n, (uint32_t)(K * sizeof(double)), bar);
+    }
+    // columns n_out .. 8 NI - 1 feed accumulators that are never stored: zero them so no NaN garbage is multiplied
+    for (int e = tid; e < (8 * NI - n_out) * ldws; e += 256) Ws[(size_t)n_out * ldws + e] = 0.0;
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    const int64_t u0 = row_begin / 16, u1 = (row_end + 15) / 16;           // 16-sample units
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    for (int64_t u = u0 + (int64_t)blockIdx.x * 8 + warp; u < u1; u += stride) {
+        const int64_t i0 = u * 16;
+        __syncwarp();
+        for (int e = lane; e < 16 * d; e += 32) { const int r = e / d, s = e - r * d; xs[r * ldx + s] = x[(i0 + r) * d + s]; }
+        for (int e = lane; e < 16 * chi; e += 32) { const int r = e / chi, a = e - r * chi; es[r * lde + a] = E[(i0 + r) * chi + a]; }
+        __syncwarp();
+        double acc[2][NI][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        // this lane's k index of the k-step: k = 4*step + fc = s + d*a
+        int a = fc / d, sidx = fc - a * d;
+        const double* xr0 = xs + fr * ldx;
+        const double* xr1 = xs + (8 + fr) * ldx;
+        const double* er0 = es + fr * lde;
+        const double* er1 = es + (8 + fr) * lde;
+        const double* wp = Ws + (size_t)fr * ldws + fc;
+#pragma unroll 4
+        for (int k0 = 0; k0 < K; k0 += 4) {
+            const bool kin = k0 + fc < K;                                  // K is a multiple of 4 in every shipped config
+            const double a0 = kin ? xr0[sidx] * er0[a] : 0.0;
+            const double a1 = kin ? xr1[sidx] * er1[a] : 0.0;
+            double b[NI];
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) b[ni] = kin ? wp[(size_t)ni * 8 * ldws + k0] : 0.0;
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) {
+                dmma_8x8x4(acc[0][ni][0], acc[0][ni][1], a0, b[ni]);
+                dmma_8x8x4(acc[1][ni][0], acc[1][ni][1], a1, b[ni]);
+            }
+            sidx += 4;
+            while (sidx >= d) { sidx -= d; a++; }
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+            const int64_t i = i0 + mi * 8 + fr;
+            if (i < row_begin || i >= row_end) continue;
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) {
+                const int n = ni * 8 + 2 * fc;
+                if (n < n_out) out[i * ldo + n] = acc[mi][ni][0];
+                if (n + 1 < n_out) out[i * ldo + n + 1] = acc[mi][ni][1];
+            }
+        }
+    }
+}
+
+template <int NI>
+int launch_reg(mpst_ctx* c, const double* x, const double* E, const double* W, double* out, int64_t row_begin,
+               int64_t row_end, int d, int chi, int n_out, int64_t ldw, int64_t ldo, size_t smem) {
+    auto kern = krao_reg_kernel<NI>;
+    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t units = (row_end + 15) / 16 - row_begin / 16;
+    const int grid = (int)std::min<int64_t>(c->sm_count, (units + 7) / 8);
+    kern<<<grid, 256, smem, c->stream>>>(x, E, W, out, row_begin, row_end, d, chi, n_out, ldw, ldo);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return MPST_OK;
+}
+
 template <int TM, int TN, int WM, int WN>
 int launch_cfg(mpst_ctx* c, const double* x, const double* E, const double* W, double* out,
                int64_t row_begin, int64_t row_end, int d, int chi, int n_out, int64_t ldw, int64_t ldo) {
@@ -165,6 +265,22 @@ int launch_krao_gemm_rows(mpst_ctx* c, const double* x, const double* E, const d
     const size_t big = 16 + sizeof(double) * ((size_t)128 * chi + (size_t)128 * d + 2 * 128 * LDP +
                                               2 * (n_out > 64 ? 128 : 64) * LDP);
 #define ARGS c, x, E, W, out, row_begin, row_end, d, chi, n_out, ldw, ldo
+    // narrow outputs with W resident in shared memory: the register-operand kernel (needs 16-byte columns, d >= 4)
+    if (n_out <= 48 && n_out >= 8 && d >= 4 && ((d * chi) % 4) == 0 && (ldw % 2) == 0 && row_end - row_begin >= 256 &&
+        !getenv("MPST_KRAO_NOREG")) {
+        const int NIc = (n_out + 7) / 8;
+        const size_t smem = 16 + sizeof(double) * ((size_t)8 * NIc * kr_pitch4(d * chi) + (size_t)8 * 16 * (kr_pitch4(d) + kr_pitch4(chi)));
+        if (smem <= 227 * 1024) {
+            switch (NIc) {
+                case 1: return launch_reg<1>(ARGS, smem);
+                case 2: return launch_reg<2>(ARGS, smem);
+                case 3: return launch_reg<3>(ARGS, smem);
+                case 4: return launch_reg<4>(ARGS, smem);
+                case 5: return launch_reg<5>(ARGS, smem);
+                default: return launch_reg<6>(ARGS, smem);
+            }
+        }
+    }
     if (big <= 227 * 1024) {
         if (n_out <= 8) return launch_cfg<128, 8, 8, 1>(ARGS);
         if (n_out <= 16) return launch_cfg<128, 16, 8, 1>(ARGS);
