@@ -18,8 +18,8 @@
 #include "dmma.cuh"
 
 namespace {
-constexpr int KC = 16;       // samples per pipeline stage
-constexpr int SR = 6;        // raw stages
+constexpr int KC = 64;       // samples per pipeline stage
+constexpr int SR = 3;        // raw stages
 
 __host__ __device__ inline int pitch4(int n) {          // smallest pitch >= n with pitch == 4 (mod 16), in doubles
     return ((n + 11) / 16) * 16 + 4;

@@ -164,7 +164,8 @@ krao_reg_kernel(const double* __restrict__ x, const double* __restrict__ E, cons
     double* es = xs + 16 * ldx;
     const int fr = lane >> 2, fc = lane & 3;
 
-    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __shared__ int next_unit;
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); next_unit = 0; }
     __syncthreads();
     if (warp == 0) {
         if (lane == 0) mbar_expect_tx(bar, (uint32_t)((size_t)n_out * K * sizeof(double)));
@@ -176,9 +177,16 @@ krao_reg_kernel(const double* __restrict__ x, const double* __restrict__ E, cons
     __syncthreads();
     mbar_wait(bar, 0);
 
-    const int64_t u0 = row_begin / 16, u1 = (row_end + 15) / 16;           // 16-sample units
-    const int64_t stride = (int64_t)gridDim.x * 8;
-    for (int64_t u = u0 + (int64_t)blockIdx.x * 8 + warp; u < u1; u += stride) {
+    // 16-sample units: a contiguous, balanced range per CTA; its warps pull the next unit from a shared counter, so
+    // every warp of the SM stays busy until the CTA's range is exhausted
+    const int64_t u0 = row_begin / 16, u1 = (row_end + 15) / 16;
+    const int64_t nun = u1 - u0;
+    const int64_t cb = u0 + nun * blockIdx.x / gridDim.x, ce = u0 + nun * (blockIdx.x + 1) / gridDim.x;
+    while (true) {
+        int64_t u = 0;
+        if (lane == 0) u = cb + atomicAdd(&next_unit, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= ce) break;
         const int64_t i0 = u * 16;
         __syncwarp();
         for (int e = lane; e < 16 * d; e += 32) { const int r = e / d, s = e - r * d; xs[r * ldx + s] = x[(i0 + r) * d + s]; }
