@@ -193,9 +193,10 @@ grad_kr_reduce_kernel(const double* __restrict__ part, const int* __restrict__ g
     const int s0 = grp_slot[grp], s1 = grp_slot[grp + 1];
     const int Dl = d * chi_l, Dr = d * chi_r;
     double* Gc = G + (size_t)cls * Dl * Dr;
-    for (int wu = 0; wu < NW; wu++) {
+    {
+        const int wu = blockIdx.y;                                 // one block per warp block of the group
         const int unit = group * NW + wu;
-        if (unit >= geo.units) break;
+        if (unit >= geo.units) return;
         int u = unit;
         const int tg = u % geo.ntg; u /= geo.ntg;
         const int sg_ = u % geo.nsg; u /= geo.nsg;
@@ -289,7 +290,7 @@ int launch_kr(mpst_ctx* c, const double* xl, const double* xr, const double* L, 
     prof_end(c, MPST_T_GRADK);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
-    grad_kr_reduce_kernel<MA, S, NB, T, NW><<<ngrp_total, 256, 0, c->stream>>>(c->part, c->tile_slot, geo, d, chi_l, chi_r, G);
+    grad_kr_reduce_kernel<MA, S, NB, T, NW><<<dim3(ngrp_total, NW), 256, 0, c->stream>>>(c->part, c->tile_slot, geo, d, chi_l, chi_r, G);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
     return MPST_OK;
