@@ -148,3 +148,19 @@ def test_sharded_gradient_allreduce_gloo(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29731", str(script), ROOT],
                          capture_output=True, text=True, env=env, timeout=240)
     assert "GLOO_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU port of the reference loop on the host cores) runs without a GPU and prints
+    one JSON line with the keys the driver reads."""
+    import json, subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "fitMPS sample-bonds/sec per sweep"
+    assert line["unit"] == "sample-bonds/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"]["workload"].startswith("trendy_sine_N100k_T100_d12_chi40")
