@@ -251,6 +251,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--samples-per-gpu", dest="n", type=int, default=0, help="override samples per GPU (debug)")
     ap.add_argument("--series-length", dest="t", type=int, default=0, help="override series length (debug)")
+    ap.add_argument("--local-dim", dest="d", type=int, default=0, help="override d (debug: config C shapes)")
+    ap.add_argument("--chi-max", dest="chi", type=int, default=0, help="override chi_max (debug: config C shapes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-impute", action="store_true")
     ap.add_argument("--impute-instances", type=int, default=2048)
@@ -265,6 +267,12 @@ def main():
         w["N"] = args.n
     if args.t:
         w["T"] = args.t
+    if args.d:
+        w["d"] = args.d
+    if args.chi:
+        w["chi_max"] = args.chi
+    if args.n or args.t or args.d or args.chi:
+        w["name"] = "trendy_sine_N%d_T%d_d%d_chi%d(debug override)" % (w["N"], w["T"], w["d"], w["chi_max"])
     N_local, T, d, chi_max = w["N"], w["T"], w["d"], w["chi_max"]
     N_global = N_local * world
     # every rank generates only its own shard: per class, rank r holds samples [r*N_local/2, (r+1)*N_local/2)
