@@ -219,7 +219,7 @@ def impute_bench(m, ctx, args):
     for i, s0 in enumerate(rng.integers(0, T - K + 1, n)):
         mask[s0:s0 + K, i] = 1
     grid = m.make_grid((-1.0, 1.0), 1e-4)
-    ctx.impute_batch(0, X[:, :64], mask[:, :64], grid)                     # warm-up
+    ctx.impute_batch(0, X[:, :256], mask[:, :256], grid)                   # warm-up (>= one instance per SM: sizes the work buffers)
     t0 = time.time()
     out = ctx.impute_batch(0, X, mask, grid, method="median")
     dt = time.time() - t0

@@ -240,6 +240,7 @@ int mpst_destroy(mpst_ctx* c) {
     auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(c->B); fr(c->G); fr(c->Z); fr(c->part); fr(c->red); fr(c->scal); fr(c->S); fr(c->gpart); fr(c->wbuf);
     fr(c->colnorm); fr(c->tmp); fr(c->meta); fr(c->sub); fr(c->gws);
+    for (int i = 0; i < 12; i++) if (c->imp_ptr[i]) cudaFree(c->imp_ptr[i]);
     if (c->hmeta) cudaFreeHost(c->hmeta);
     if (c->perm) cudaFree(c->perm);
     if (c->flags) cudaFree(c->flags);

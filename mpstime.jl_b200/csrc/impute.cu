@@ -20,6 +20,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
 #include "mpst_common.cuh"
 #include "dmma.cuh"
 #include "encode_device.cuh"
@@ -246,21 +248,13 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
     double* GR = P.gr_scratch + (size_t)blockIdx.x * P.Kmax * P.chimax * P.chimax;
     double* pbuf = P.p_scratch + (size_t)blockIdx.x * G;
 
-    // out[i] = sum_j As[i][j] * v[j]  (ROWS) or out[j] = sum_i v[i] As[i][j] (COLS), accumulated with weight wgt
-    // into acc[] (per-thread partials over its quarter of the contracted index); finished by reduce_partials.
-    auto contract_rows = [&](double wgt, int cl, int cr, double* acc) {      // index i = l64 (+64), group splits j
-        const int j0 = grp * ((cr + 3) / 4), j1 = min(cr, j0 + (cr + 3) / 4);
-        for (int q = 0, i = l64; i < cl; i += 64, q++) {
+    // acc[q] += wgt * sum_a vec[a] * src[a*cr + j],  j = l64 + 64 q, straight from global memory (whole contraction
+    // index per thread: no cross-group reduction)
+    auto colsum_global = [&](const double* __restrict__ src, int cl, int cr, double wgt, double* acc) {
+        for (int q = 0, jj = l64; jj < cr; jj += 64, q++) {
             double t = 0.0;
-            for (int j = j0; j < j1; j++) t += As[i * ld + j] * vec[j];
-            acc[q] += wgt * t;
-        }
-    };
-    auto contract_cols = [&](double wgt, int cl, int cr, double* acc) {      // index j = l64 (+64), group splits i
-        const int i0 = grp * ((cl + 3) / 4), i1 = min(cl, i0 + (cl + 3) / 4);
-        for (int q = 0, j = l64; j < cr; j += 64, q++) {
-            double t = 0.0;
-            for (int i = i0; i < i1; i++) t += vec[i] * As[i * ld + j];
+#pragma unroll 8
+            for (int a = 0; a < cl; a++) t = fma(vec[a], __ldg(src + (size_t)a * cr + jj), t);
             acc[q] += wgt * t;
         }
     };
@@ -306,15 +300,22 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
             const int cl = P.chi[j], cr = P.chi[j + 1];
             if (tid == 0) encode_any(P.basis, x[j], d, phi);
             const double* A = P.cores + P.core_off[j];           // [s][a][b]
-            double acc[2] = {0.0, 0.0};
-            for (int s = 0; s < d; s++) {
-                __syncthreads();
-                stage_slice(As, A, s, cl, cr, n8, ld);
-                __syncthreads();
-                contract_rows(phi[s], cl, cr, acc);               // r'[a] += phi_s sum_b A_s[a][b] r[b]
+            __syncthreads();
+            // r'[a] = sum_s phi_s sum_b A_s[a][b] r[b]: one row a per warp at a time, lanes along b (coalesced reads
+            // straight from global memory -- every core element is used once), one shuffle reduction per row
+            for (int a = tid >> 5; a < cl; a += NT / 32) {
+                double t = 0.0;
+                for (int s = 0; s < d; s++) {
+                    const double* row = A + ((size_t)s * cl + a) * cr;
+                    double ts = 0.0;
+                    for (int b = tid & 31; b < cr; b += 32) ts = fma(__ldg(row + b), vec[b], ts);
+                    t = fma(phi[s], ts, t);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if ((tid & 31) == 0) vec2[a] = t;
             }
             __syncthreads();
-            reduce_partials(acc, cl, vec2);
             normalise_into_vec(cl);
         }
         TOCK(0);
@@ -388,28 +389,23 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                 TICK();
                 if (!mk[j]) {
                     if (tid == 0) encode_any(P.basis, x[j], d, phi);
-                    double acc[2] = {0.0, 0.0};
-                    for (int s = 0; s < d; s++) {
-                        __syncthreads();
-                        stage_slice(As, A, s, cl, cr, n8, ld);
-                        __syncthreads();
-                        contract_cols(phi[s], cl, cr, acc);           // v'[b] += phi_s sum_a v[a] A_s[a][b]
-                    }
                     __syncthreads();
+                    // v'[b] = sum_s phi_s sum_a v[a] A_s[a][b]: every core element is used once, so it is read straight
+                    // from global memory (coalesced over b, loads batched); the 4 thread groups take the slices s = g mod 4
+                    double acc[2] = {0.0, 0.0};
+                    for (int s = grp; s < d; s += 4) colsum_global(A + (size_t)s * cl * cr, cl, cr, phi[s], acc);
                     reduce_partials(acc, cr, vec2);
                     x_prev = x[j];
                     have_prev = true;
                     TOCK(2);
                 } else {
                     // A_d[s][b] = sum_a v[a] A[s][a][b]
-                    for (int s = 0; s < d; s++) {
-                        __syncthreads();
-                        stage_slice(As, A, s, cl, cr, n8, ld);
-                        __syncthreads();
+                    for (int s = grp; s < d; s += 4) {                // one slice per thread group, no reduction needed
                         double acc[2] = {0.0, 0.0};
-                        contract_cols(1.0, cl, cr, acc);
-                        reduce_partials(acc, cr, Ad + s * ld);
+                        colsum_global(A + (size_t)s * cl * cr, cl, cr, 1.0, acc);
+                        for (int q = 0, jj = l64; jj < cr; jj += 64, q++) Ad[s * ld + jj] = acc[q];
                     }
+                    __syncthreads();
                     TOCK(3);
                     TICK();
                     const double* Gk = GR + (size_t)k * P.chimax * P.chimax;
@@ -599,6 +595,7 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
         off[j] = tot;
         tot += (int64_t)d * k.chi_l * k.chi_r;
     }
+    const auto t_begin = std::chrono::steady_clock::now();
     const int n8 = (chimax + 7) & ~7, ld = n8 + 4;
     const size_t smem = sizeof(double) * ((size_t)4 * n8 * ld + 2 * n8 + 2 * (size_t)d * ld + 2 * (size_t)d * d + MPST_MAX_D + 32 +
                                           std::max(3 * NT + 16, 4 * n8) + MPST_MAX_D * MPST_MAX_D);
@@ -607,29 +604,34 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     int Kmax = 0;
     for (int64_t i = 0; i < n; i++) { int k = 0; for (int j = 0; j < T; j++) k += missing[i * T + j] ? 1 : 0; Kmax = std::max(Kmax, k); }
     if (Kmax == 0) { for (int64_t i = 0; i < n; i++) for (int tr = 0; tr < n_traj; tr++) memcpy(out + (i * n_traj + tr) * T, X + i * T, sizeof(double) * T); return MPST_OK; }
-    const int grid = (int)std::min<int64_t>(n, 2 * (int64_t)c->sm_count);
+    const int grid = (int)std::min<int64_t>(n, (int64_t)c->sm_count);       // one resident CTA per SM (shared memory), instances strided
     double *dcores = nullptr, *dX = nullptr, *dgrid = nullptr, *dgenc = nullptr, *dunif = nullptr, *dout = nullptr, *dGR = nullptr, *dp = nullptr;
     uint8_t* dmask = nullptr;
     int64_t* doff = nullptr;
     int* dchi = nullptr;
     int rc = MPST_OK;
-    auto cleanup = [&]() {
-        cudaFree(dcores); cudaFree(dX); cudaFree(dgrid); cudaFree(dgenc); cudaFree(dunif); cudaFree(dout); cudaFree(dGR); cudaFree(dp);
-        cudaFree(dmask); cudaFree(doff); cudaFree(dchi);
-    };
+    auto cleanup = [&]() {};                                       // buffers belong to the context (freed by mpst_destroy)
 #define IMP_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { c->err = std::string(#expr) + ": " + cudaGetErrorString(_e); cleanup(); return MPST_E_CUDA; } } while (0)
-    IMP_TRY(cudaMalloc(&dcores, sizeof(double) * tot));
-    IMP_TRY(cudaMalloc(&dX, sizeof(double) * n * T));
-    IMP_TRY(cudaMalloc(&dmask, (size_t)n * T));
-    IMP_TRY(cudaMalloc(&dgrid, sizeof(double) * G));
-    IMP_TRY(cudaMalloc(&dgenc, sizeof(double) * (size_t)G * d));
-    IMP_TRY(cudaMalloc(&dout, sizeof(double) * n * n_traj * T));
-    IMP_TRY(cudaMalloc(&dGR, sizeof(double) * ((size_t)grid * Kmax * chimax * chimax + 64)));
-    IMP_TRY(cudaMalloc(&dp, sizeof(double) * (size_t)grid * G));
-    IMP_TRY(cudaMalloc(&doff, sizeof(int64_t) * T));
-    IMP_TRY(cudaMalloc(&dchi, sizeof(int) * (T + 1)));
+    // grow-only work buffers held by the context: a second call of the same shape pays for copies only
+    auto reserve = [&](int slot, size_t bytes, void** out) -> cudaError_t {
+        if (c->imp_ptr[slot] && c->imp_cap[slot] >= bytes) { *out = c->imp_ptr[slot]; return cudaSuccess; }
+        if (c->imp_ptr[slot]) { cudaFree(c->imp_ptr[slot]); c->imp_ptr[slot] = nullptr; c->imp_cap[slot] = 0; }
+        cudaError_t e = cudaMalloc(&c->imp_ptr[slot], bytes);
+        if (e == cudaSuccess) { c->imp_cap[slot] = bytes; *out = c->imp_ptr[slot]; }
+        return e;
+    };
+    IMP_TRY(reserve(0, sizeof(double) * tot, (void**)&dcores));
+    IMP_TRY(reserve(1, sizeof(double) * n * T, (void**)&dX));
+    IMP_TRY(reserve(2, (size_t)n * T, (void**)&dmask));
+    IMP_TRY(reserve(3, sizeof(double) * G, (void**)&dgrid));
+    IMP_TRY(reserve(4, sizeof(double) * (size_t)G * d, (void**)&dgenc));
+    IMP_TRY(reserve(5, sizeof(double) * n * n_traj * T, (void**)&dout));
+    IMP_TRY(reserve(6, sizeof(double) * ((size_t)grid * Kmax * chimax * chimax + 64), (void**)&dGR));
+    IMP_TRY(reserve(7, sizeof(double) * (size_t)grid * G, (void**)&dp));
+    IMP_TRY(reserve(8, sizeof(int64_t) * T, (void**)&doff));
+    IMP_TRY(reserve(9, sizeof(int) * (T + 1), (void**)&dchi));
     if (uniforms) {
-        IMP_TRY(cudaMalloc(&dunif, sizeof(double) * n * n_traj * Kmax));
+        IMP_TRY(reserve(10, sizeof(double) * n * n_traj * Kmax, (void**)&dunif));
         IMP_TRY(cudaMemcpyAsync(dunif, uniforms, sizeof(double) * n * n_traj * Kmax, cudaMemcpyHostToDevice, c->stream));
     }
     IMP_TRY(cudaMemcpyAsync(dX, X, sizeof(double) * n * T, cudaMemcpyHostToDevice, c->stream));
@@ -664,6 +666,7 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
         IMP_TRY(cudaStreamSynchronize(c->stream));                                 // ha/hb are stack temporaries
     }
     IMP_TRY(cudaFuncSetAttribute(impute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const auto t_setup = std::chrono::steady_clock::now();
     prof_begin(c, MPST_T_IMPUTE);
     impute_kernel<<<grid, NT, smem, c->stream>>>(P);
     prof_end(c, MPST_T_IMPUTE);
@@ -671,6 +674,12 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     IMP_TRY(cudaGetLastError());
     IMP_TRY(cudaMemcpyAsync(out, dout, sizeof(double) * n * n_traj * T, cudaMemcpyDeviceToHost, c->stream));
     IMP_TRY(cudaStreamSynchronize(c->stream));
+    if (P.debug) {
+        const auto t_end = std::chrono::steady_clock::now();
+        fprintf(stderr, "[impute host] setup %.1f ms, kernel + copy back %.1f ms (grid %d, n %lld)\n",
+                1e3 * std::chrono::duration<double>(t_setup - t_begin).count(),
+                1e3 * std::chrono::duration<double>(t_end - t_setup).count(), grid, (long long)n);
+    }
 #undef IMP_TRY
     cleanup();
     return MPST_OK;

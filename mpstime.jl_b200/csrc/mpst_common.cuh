@@ -89,6 +89,8 @@ struct mpst_ctx {
     double* sub = nullptr;      // subspace-SVD workspace
     size_t subcap = 0;
     double* gws = nullptr;      // split-K partial products of the small GEMMs
+    void* imp_ptr[12] = {nullptr};   // imputation work buffers (grow-only, reused across mpst_impute_batch calls)
+    size_t imp_cap[12] = {0};
     // per-bond subspace-iteration count learned during training (svd_subspace.cu): svd_slot = bond being split
     // (-1: none), svd_its[b] = iterations to start with, svd_floor[b] = smallest count that has not failed yet
     // provenance of the environment slots: slot j is reusable as the unlabelled forward factor of a bond when it

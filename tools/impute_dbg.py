@@ -15,6 +15,7 @@ mask = np.zeros((T, n), dtype=np.uint8)
 for i, s0 in enumerate(rng.integers(0, T - K + 1, n)):
     mask[s0:s0 + K, i] = 1
 grid = m.make_grid((-1.0, 1.0), dx)
+ctx.impute_batch(0, X[:, :256], mask[:, :256], grid, method="median")   # warm-up
 t0 = time.time()
 out = ctx.impute_batch(0, X, mask, grid, method="median")
 print("ok", out.shape, time.time() - t0, np.isfinite(out).all())
