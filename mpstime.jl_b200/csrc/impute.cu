@@ -305,11 +305,14 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
             // straight from global memory -- every core element is used once), one shuffle reduction per row
             for (int a = tid >> 5; a < cl; a += NT / 32) {
                 double t = 0.0;
-                for (int s = 0; s < d; s++) {
-                    const double* row = A + ((size_t)s * cl + a) * cr;
-                    double ts = 0.0;
-                    for (int b = tid & 31; b < cr; b += 32) ts = fma(__ldg(row + b), vec[b], ts);
-                    t = fma(phi[s], ts, t);
+                const double* row0 = A + (size_t)a * cr;
+                const size_t sstride = (size_t)cl * cr;
+                for (int b = tid & 31; b < cr; b += 32) {
+                    const double vb = vec[b];
+                    double tb = 0.0;
+#pragma unroll 8
+                    for (int s = 0; s < d; s++) tb = fma(phi[s], __ldg(row0 + s * sstride + b), tb);   // d loads in flight
+                    t = fma(tb, vb, t);
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
@@ -487,10 +490,11 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                         double best = 1e300;
                         int bg = 0x7fffffff;
                         double run = pre_t;
+                        const double uZ = u * Z;
                         for (int g = g0; g < g1; g++) {
                             if (g > 0) run += pbuf[g - 1] + pbuf[g];
                             const double cg = h * run;
-                            const double val = fabs(cg / Z - u);
+                            const double val = fabs(cg - uZ);            // argmin |cdf/Z - u| without a division per point
                             if (val < best) { best = val; bg = g; }
                         }
                         gsel = block_argbest<false>(best, bg, scr);
