@@ -54,41 +54,52 @@ __device__ __forceinline__ void encode_any(int basis, double x, int d, double* v
 
 // C[n8 x n8] (+)= A * B  (or A * B^T when TB) on the FP64 tensor cores; all operands in shared memory with pitch
 // ld == 4 (mod 16) doubles (conflict-free DMMA fragment loads), dimensions padded with zeros to a multiple of 8.
-// 8 warps; each warp owns 8x8 output blocks in a strided fashion.
+// 8 warps as 4 (block-row pairs) x 2 (block-column quads).
 template <bool TB, bool ACC>
 __device__ __forceinline__ void smem_dmma_matmul(double* __restrict__ Cm, const double* __restrict__ A,
                                                  const double* __restrict__ B, int n8, int ld) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int fr = lane >> 2, fc = lane & 3;
     const int nb = n8 >> 3;
-    // each warp: block rows i = warp, warp+8, ... ; all block columns, two at a time
-    for (int bi = warp; bi < nb; bi += 8) {
-        for (int bj = 0; bj < nb; bj += 8) {
-            double c[8][2];
+    // warp (wr, wc) owns 2 block rows x 4 block columns at a time: per k-step 2 A + 4 B fragment loads feed 8 DMMAs
+    // (the 1 x 8 blocking this replaces needed 9 loads for 8 DMMAs and made every warp stream all of B)
+    const int wr = warp >> 1, wc = warp & 1;
+    for (int bi = 2 * wr; bi < nb; bi += 8) {
+        const bool r1 = bi + 1 < nb;
+        for (int bj = 4 * wc; bj < nb; bj += 8) {
+            double c[2][4][2];
 #pragma unroll
-            for (int t = 0; t < 8; t++) {
-                const int j = (bj + t) * 8 + 2 * fc;
-                if (ACC && bj + t < nb) { c[t][0] = Cm[(bi * 8 + fr) * ld + j]; c[t][1] = Cm[(bi * 8 + fr) * ld + j + 1]; }
-                else { c[t][0] = 0.0; c[t][1] = 0.0; }
-            }
+            for (int u = 0; u < 2; u++)
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int i = (bi + u) * 8 + fr, j = (bj + t) * 8 + 2 * fc;
+                    if (ACC && bi + u < nb && bj + t < nb) { c[u][t][0] = Cm[i * ld + j]; c[u][t][1] = Cm[i * ld + j + 1]; }
+                    else { c[u][t][0] = 0.0; c[u][t][1] = 0.0; }
+                }
+            const double* a0p = A + (bi * 8 + fr) * ld + fc;
+            const double* a1p = A + ((r1 ? bi + 1 : bi) * 8 + fr) * ld + fc;
+#pragma unroll 2
             for (int k0 = 0; k0 < n8; k0 += 4) {
-                const double av = A[(bi * 8 + fr) * ld + k0 + fc];
+                const double av0 = a0p[k0], av1 = a1p[k0];
 #pragma unroll
-                for (int t = 0; t < 8; t++) {
+                for (int t = 0; t < 4; t++) {
                     if (bj + t < nb) {
                         const int jb = (bj + t) * 8;
                         const double bv = TB ? B[(jb + fr) * ld + k0 + fc] : B[(k0 + fc) * ld + jb + fr];
-                        dmma_8x8x4(c[t][0], c[t][1], av, bv);
+                        dmma_8x8x4(c[0][t][0], c[0][t][1], av0, bv);
+                        dmma_8x8x4(c[1][t][0], c[1][t][1], av1, bv);
                     }
                 }
             }
 #pragma unroll
-            for (int t = 0; t < 8; t++)
-                if (bj + t < nb) {
-                    const int j = (bj + t) * 8 + 2 * fc;
-                    Cm[(bi * 8 + fr) * ld + j] = c[t][0];
-                    Cm[(bi * 8 + fr) * ld + j + 1] = c[t][1];
-                }
+            for (int u = 0; u < 2; u++)
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (bi + u < nb && bj + t < nb) {
+                        const int i = (bi + u) * 8 + fr, j = (bj + t) * 8 + 2 * fc;
+                        Cm[i * ld + j] = c[u][t][0];
+                        Cm[i * ld + j + 1] = c[u][t][1];
+                    }
         }
     }
 }
@@ -456,7 +467,7 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                         }
                         __syncthreads();
                         if (D == 8) pdf_legendre<8, 4>(Rm, P.grid, g0, g1, pbuf);
-                        else if (D == 16) pdf_legendre<16, 2>(Rm, P.grid, g0, g1, pbuf);
+                        else if (D == 16) pdf_legendre<16, 4>(Rm, P.grid, g0, g1, pbuf);
                         else if (D == 24) pdf_legendre<24, 2>(Rm, P.grid, g0, g1, pbuf);
                         else pdf_legendre<32, 2>(Rm, P.grid, g0, g1, pbuf);
                     } else {
