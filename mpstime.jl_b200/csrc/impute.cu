@@ -42,6 +42,7 @@ struct ImpParams {
     double* gr_scratch;         // [grid][Kmax][chimax^2]
     double* p_scratch;          // [grid][G]
     int T, d, G, ntraj, Kmax, chimax, method, basis, debug;
+    int dbuf;                       // 1: a second slice buffer fits in shared memory (asynchronous double-buffered staging)
     int64_t n;
     double max_jump;
 };
@@ -233,6 +234,21 @@ __device__ __forceinline__ void stage_slice(double* __restrict__ As, const doubl
         for (int b = lane; b < n8; b += 32) As[a * ld + b] = (a < cl && b < cr) ? src[a * cr + b] : 0.0;
 }
 
+// asynchronous variant: 16-byte cp.async chunks of the valid cl x cr region (cr even, 16-byte aligned rows); the zero
+// padding of the buffer is written once per site by the caller
+__device__ __forceinline__ void stage_slice_async(double* __restrict__ As, const double* __restrict__ A, int s, int cl, int cr,
+                                                  int ld) {
+    const double* src = A + (size_t)s * cl * cr;
+    const int half = cr >> 1;                          // 16-byte chunks per row
+    for (int e = threadIdx.x; e < cl * half; e += NT) {
+        const int a = e / half, b2 = e - a * half;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(As + a * ld + 2 * b2);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)a * cr + 2 * b2) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
     extern __shared__ double sm[];
     const int n8 = (P.chimax + 7) & ~7;
@@ -252,6 +268,7 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
     double* red = phi + MPST_MAX_D;                    // [32] reductions
     double* scr = red + 32;                            // [max(3*NT + 16, 4*n8)] scan / partial-sum scratch
     double* pdfR = scr + max(3 * NT + 16, 4 * n8);     // [32*32] rho * normalisation for the Legendre pdf
+    double* As2 = pdfR + MPST_MAX_D * MPST_MAX_D;      // second slice buffer (only when P.dbuf)
     __shared__ int s_misc[4];
     const int tid = threadIdx.x;
     const int T = P.T, d = P.d, G = P.G;
@@ -352,13 +369,31 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                 kidx--;
                 if (j == first) break;
                 for (int e = tid; e < n8 * n8; e += NT) Gn[(e / n8) * ld + (e % n8)] = 0.0;
-                for (int s = 0; s < d; s++) {
+                if (P.dbuf && !(cr & 1) && !((cl * cr) & 1) && !(P.core_off[j] & 1)) {
+                    // double-buffered: slice s+1 streams in (cp.async) while the two products of slice s run
                     __syncthreads();
-                    stage_slice(As, A, s, cl, cr, n8, ld);
+                    if (cl < n8 || cr < n8)
+                        for (int e = tid; e < n8 * n8; e += NT) { const int o = (e / n8) * ld + (e % n8); As[o] = 0.0; As2[o] = 0.0; }
                     __syncthreads();
-                    smem_dmma_matmul<false, false>(T1, As, Gm, n8, ld);        // T1 = A_s G
-                    __syncthreads();
-                    smem_dmma_matmul<true, true>(Gn, T1, As, n8, ld);          // Gn += T1 A_s^T
+                    stage_slice_async(As, A, 0, cl, cr, ld);
+                    for (int s = 0; s < d; s++) {
+                        double* cur = (s & 1) ? As2 : As;
+                        stage_wait_all();
+                        __syncthreads();                                       // slice s visible, products of slice s-1 done
+                        if (s + 1 < d) stage_slice_async((s & 1) ? As : As2, A, s + 1, cl, cr, ld);
+                        smem_dmma_matmul<false, false>(T1, cur, Gm, n8, ld);   // T1 = A_s G
+                        __syncthreads();
+                        smem_dmma_matmul<true, true>(Gn, T1, cur, n8, ld);     // Gn += T1 A_s^T
+                    }
+                } else {
+                    for (int s = 0; s < d; s++) {
+                        __syncthreads();
+                        stage_slice(As, A, s, cl, cr, n8, ld);
+                        __syncthreads();
+                        smem_dmma_matmul<false, false>(T1, As, Gm, n8, ld);    // T1 = A_s G
+                        __syncthreads();
+                        smem_dmma_matmul<true, true>(Gn, T1, As, n8, ld);      // Gn += T1 A_s^T
+                    }
                 }
             } else {
                 if (tid == 0) encode_any(P.basis, x[j], d, phi);
@@ -612,8 +647,10 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     }
     const auto t_begin = std::chrono::steady_clock::now();
     const int n8 = (chimax + 7) & ~7, ld = n8 + 4;
-    const size_t smem = sizeof(double) * ((size_t)4 * n8 * ld + 2 * n8 + 2 * (size_t)d * ld + 2 * (size_t)d * d + MPST_MAX_D + 32 +
-                                          std::max(3 * NT + 16, 4 * n8) + MPST_MAX_D * MPST_MAX_D);
+    size_t smem = sizeof(double) * ((size_t)4 * n8 * ld + 2 * n8 + 2 * (size_t)d * ld + 2 * (size_t)d * d + MPST_MAX_D + 32 +
+                                    std::max(3 * NT + 16, 4 * n8) + MPST_MAX_D * MPST_MAX_D);
+    const bool dbuf = smem + sizeof(double) * (size_t)n8 * ld <= 227 * 1024 && !getenv("MPST_IMPUTE_NODBUF");
+    if (dbuf) smem += sizeof(double) * (size_t)n8 * ld;
     if (smem > 227 * 1024) { c->err = "impute_batch: chi too large for the shared-memory Gram matrices (chi <= 72 at d = 16)"; return MPST_E_UNSUPPORTED; }
     // host-side Kmax
     int Kmax = 0;
@@ -672,6 +709,7 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     P.T = T; P.d = d; P.G = G; P.ntraj = n_traj; P.Kmax = Kmax; P.chimax = chimax; P.method = method; P.basis = c->basis;
     P.n = n; P.max_jump = max_jump;
     P.debug = getenv("MPST_IMPUTE_DEBUG") ? 1 : 0;
+    P.dbuf = dbuf ? 1 : 0;
     {
         double ha[MPST_MAX_D], hb[MPST_MAX_D];
         ha[0] = hb[0] = 0.0;
