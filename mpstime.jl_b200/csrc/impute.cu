@@ -526,7 +526,14 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                     if (P.method == MPST_IMPUTE_MEDIAN || P.method == MPST_IMPUTE_ITS) {
                         // cumulative trapezoid c[g] = c[g-1] + (p[g-1] + p[g]), scaled by h = (x1-x0)/2
                         double loc = 0.0;
-                        for (int g = max(g0, 1); g < g1; g++) loc += pbuf[g - 1] + pbuf[g];
+                        {
+                            double prev = (g0 > 0 && g0 < g1) ? pbuf[g0 - 1] : 0.0;          // every value is read once
+                            for (int g = g0; g < g1; g++) {
+                                const double cur = pbuf[g];
+                                if (g > 0) loc += prev + cur;
+                                prev = cur;
+                            }
+                        }
                         double tot;
                         const double pre_t = block_excl_scan(loc, scr, tot);
                         const double h = (P.grid[1] - P.grid[0]) * 0.5;
@@ -537,8 +544,11 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                         int bg = 0x7fffffff;
                         double run = pre_t;
                         const double uZ = u * Z;
+                        double prev = (g0 > 0 && g0 < g1) ? pbuf[g0 - 1] : 0.0;
                         for (int g = g0; g < g1; g++) {
-                            if (g > 0) run += pbuf[g - 1] + pbuf[g];
+                            const double cur = pbuf[g];
+                            if (g > 0) run += prev + cur;
+                            prev = cur;
                             const double cg = h * run;
                             const double val = fabs(cg - uZ);            // argmin |cdf/Z - u| without a division per point
                             if (val < best) { best = val; bg = g; }
