@@ -36,8 +36,8 @@ FP64_PEAK_TFLOPS = 35.4      # cuBLAS DGEMM measured on this pool (profiles/r01_
 FP64_PEAK_NOTE = "fallback: same-pool cuBLAS DGEMM 8192^3 = 35.4 TFLOP/s (DMMA issue peak 37.1); MEASURED_PEAKS.json carries no FP64 figure"
 # dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch of the gradient kernel at config B shapes
 # (ncu --set full, profiles/r01_bond_grad_kr_ncu_full.txt); algorithmic bytes are 84 MB, the kernel is tensor bound
-NCU_TRAFFIC_BYTES = 258.4e6
-NCU_TRAFFIC_NOTE = "profiles/r01_bond_grad_kr_ncu_full.txt (ncu --set full, launch 60 of a config-B sweep): 250.4 MB read + 8.0 MB written"
+NCU_TRAFFIC_BYTES = 184.6e6
+NCU_TRAFFIC_NOTE = "profiles/r01_bond_grad_kr_ncu_full.txt (ncu --set full, launch 30 of a config-B sweep): 175.5 MB read + 9.1 MB written"
 
 
 def trendy_sine(T, n, period, slopes, sigma, rng):
