@@ -314,6 +314,7 @@ static int model_reset(mpst_ctx* c, int T, int C, int d, int chi_max) {
     c->env_dir.assign(T, 0);
     c->svd_its.clear();
     c->svd_floor.clear();
+    c->svd_nohalf.clear();
     if ((int)c->cores.size() != T) {
         for (auto& k : c->cores) if (k.dev) cudaFree(k.dev);
         c->cores.assign(T, Core());
@@ -687,7 +688,7 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         const size_t cap = (size_t)d * c->chi_max * c->chi_max * C;
         TRY(core_reserve(c, klabel, cap));
         TRY(core_reserve(c, kortho, cap));
-        if ((int)c->svd_its.size() != c->T) { c->svd_its.assign(c->T, 0); c->svd_floor.assign(c->T, 0); }
+        if ((int)c->svd_its.size() != c->T) { c->svd_its.assign(c->T, 0); c->svd_floor.assign(c->T, 0); c->svd_nohalf.assign(c->T, 0); }
         c->svd_slot = l;
         const int rc_svd = svd_split_device(c, c->B, Dl, Dr, C, going_left, o->chi_max, o->cutoff, norm2_dev, klabel.dev,
                                             kortho.dev, &chi_new, nullptr, nullptr);

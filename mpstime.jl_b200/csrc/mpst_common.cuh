@@ -100,6 +100,7 @@ struct mpst_ctx {
     std::vector<int> env_dir;
     int svd_slot = -1;
     std::vector<int> svd_its, svd_floor;
+    std::vector<char> svd_nohalf;   // bonds on which the column-scaling shortcut of the subspace iteration broke down once
     // capacities (doubles) of the training buffers: a re-load with the same or a smaller shape reuses them
     size_t cap_X = 0, cap_PHI = 0, cap_phi = 0, cap_env = 0, cap_ones = 0, cap_yw = 0;
     size_t gwscap = 0;

@@ -396,6 +396,26 @@ int launch_sym_eig(int p, size_t smem, const double* H, int splits, int q, doubl
     }
 }
 
+// out[:, j] = in[:, j] / ||in[:, j]||  (one block per column).  Replaces the Cholesky-QR of Z = M Q in the later
+// subspace iterations: with Q close to the singular vectors the columns of Z are nearly orthogonal already and only
+// their norms (sigma_j) differ by orders of magnitude.
+__global__ void __launch_bounds__(256)
+colscale_kernel(const double* __restrict__ in, double* __restrict__ out, int rows) {
+    __shared__ double sh[8];
+    const double* x = in + (size_t)blockIdx.x * rows;
+    double* y = out + (size_t)blockIdx.x * rows;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < rows; i += 256) s = fma(x[i], x[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += sh[w];
+    const double inv = t > 0.0 ? rsqrt(t) : 0.0;
+    for (int i = threadIdx.x; i < rows; i += 256) y[i] = x[i] * inv;
+}
+
 // rank the p Ritz values, apply the NDTensors truncation rule with the weight outside the subspace
 // (trace - sum) already discarded; perm[k] = column of the k-th largest, Psorted, iscal[0] = chi_new.
 __global__ void __launch_bounds__(256)
@@ -613,6 +633,12 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     // (kappa ~ (sqrt(n)+sqrt(p))/(sqrt(n)-sqrt(p))) and only its span matters
     const int max_rounds = 3;
     int iters_done = 0;
+    // Column-scaling shortcut (training sweeps only): from the third iteration on Z = M Q is only column-normalised
+    // instead of orthonormalised.  If that ever makes a Cholesky pivot break down on a bond, the bond is flagged and
+    // this call restarts with full orthonormalisation, so the shortcut can cost time but never correctness.
+    const int slot0 = (c->svd_slot >= 0 && c->svd_slot < (int)c->svd_its.size()) ? c->svd_slot : -1;
+    bool half_orth = slot0 >= 0 && !c->svd_nohalf[slot0] && !getenv("MPST_SVD_NOHALF");
+restart:
     for (int round = 0; round < max_rounds; round++) {
         // iterations of the first round: 5 unless this bond's previous visits showed that fewer reach the residual
         // bound (trained spectra change slowly from sweep to sweep); a visit that needs a second round raises the
@@ -623,7 +649,12 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         const int niter = round == 0 ? first : 3;
         for (int it = 0; it < niter; it++) {
             TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, Qa, n, Za, m));            // Z = M Q
-            TRY(cholqr(Za, Zb, m));
+            if (half_orth && iters_done >= 2) {
+                colscale_kernel<<<p, 256, 0, c->stream>>>(Za, Zb, m);
+                c->launches++;
+            } else {
+                TRY(cholqr(Za, Zb, m));
+            }
             TRY(launch_dgemm(c, 1, 0, n, p, m, M, ldm, Zb, m, Qb, n));            // Y = M^T Z
             TRY(cholqr(Qb, Qa, n));
             iters_done++;
@@ -656,6 +687,17 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         const double res = c->hscal[10];
         if (c->hiscal[8] != 0 || !(res == res)) {
+            if (half_orth) {                                                       // retry once without the shortcut
+                if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d breakdown with column scaling -> restart with full orth\n", m, n);
+                c->svd_nohalf[slot0] = 1;
+                half_orth = false;
+                iters_done = 0;
+                CUDA_TRY(c, cudaMemsetAsync(status, 0, sizeof(int), c->stream));
+                const int64_t tot = (int64_t)n * p;
+                rand_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(Qa, n, p, n, 0x5DEECE66Dull + (uint64_t)m * 131 + n);
+                c->launches++;
+                goto restart;
+            }
             if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d breakdown status=%d -> full Jacobi\n", m, n, c->hiscal[8]);
             return MPST_OK;
         }
