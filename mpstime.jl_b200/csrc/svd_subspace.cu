@@ -633,11 +633,12 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     // (kappa ~ (sqrt(n)+sqrt(p))/(sqrt(n)-sqrt(p))) and only its span matters
     const int max_rounds = 3;
     int iters_done = 0;
-    // Column-scaling shortcut (training sweeps only): from the third iteration on Z = M Q is only column-normalised
+    // Column-scaling shortcut (training sweeps only): from the second iteration on Z = M Q is only column-normalised
     // instead of orthonormalised.  If that ever makes a Cholesky pivot break down on a bond, the bond is flagged and
     // this call restarts with full orthonormalisation, so the shortcut can cost time but never correctness.
     const int slot0 = (c->svd_slot >= 0 && c->svd_slot < (int)c->svd_its.size()) ? c->svd_slot : -1;
     bool half_orth = slot0 >= 0 && !c->svd_nohalf[slot0] && !getenv("MPST_SVD_NOHALF");
+    const int half_from = getenv("MPST_SVD_HALF_FROM") ? atoi(getenv("MPST_SVD_HALF_FROM")) : 1;
 restart:
     for (int round = 0; round < max_rounds; round++) {
         // iterations of the first round: 5 unless this bond's previous visits showed that fewer reach the residual
@@ -649,7 +650,7 @@ restart:
         const int niter = round == 0 ? first : 3;
         for (int it = 0; it < niter; it++) {
             TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, Qa, n, Za, m));            // Z = M Q
-            if (half_orth && iters_done >= 2) {
+            if (half_orth && iters_done >= half_from) {
                 colscale_kernel<<<p, 256, 0, c->stream>>>(Za, Zb, m);
                 c->launches++;
             } else {
