@@ -7,8 +7,8 @@
 // T sites) block of G: its A/B fragments come straight from the raw L / R rows that the bulk-TMA ring delivers,
 // and are scaled in registers by the per-sample site values (MA*S + NB*T multiplies for MA*S*NB*T DMMAs per
 // k-step of 4 samples; the sample weight rides on the A fragment).  No operand tiles, no block barrier: warp 0
-// issues the TMA copies two chunks ahead (row by row into a pitch == 4 (mod 16) layout, so fragment loads are
-// conflict free), every warp waits on the stage's full-mbarrier and releases it on the empty-mbarrier.
+// issues the bulk-TMA copies of the next 64-sample stage (3-stage ring), every warp waits on the stage's
+// full-mbarrier and releases it on the empty-mbarrier.
 // Schedule: stream-K over (class, group of 8 warp blocks, 16-sample chunk), one contiguous range per CTA
 // (grid = #SMs), deterministic segment reduction in a second kernel, exactly as in bond_grad.cu.
 #include <algorithm>
@@ -20,10 +20,6 @@
 namespace {
 constexpr int KC = 64;       // samples per pipeline stage
 constexpr int SR = 3;        // raw stages
-
-__host__ __device__ inline int pitch4(int n) {          // smallest pitch >= n with pitch == 4 (mod 16), in doubles
-    return ((n + 11) / 16) * 16 + 4;
-}
 
 struct KrGeom {
     int nab, nsg, nbb, ntg;  // link blocks / site groups per side
@@ -37,12 +33,15 @@ bond_grad_kr_kernel(const double* __restrict__ xl, const double* __restrict__ xr
                     const double* __restrict__ L, const double* __restrict__ R,
                     const double* __restrict__ w, int64_t wstride, int d, int chi_l, int chi_r, KrGeom geo,
                     const GradSeg* __restrict__ segs, const int* __restrict__ cta_ptr,
-                    double* __restrict__ part, int rowwise, int LOOK) {
+                    double* __restrict__ part) {
     extern __shared__ __align__(16) unsigned char smraw[];
     uint64_t* raw_full = reinterpret_cast<uint64_t*>(smraw);      // [SR] TMA landed
     uint64_t* raw_empty = raw_full + SR;                          // [SR] all 8 warps done reading
     double* base = reinterpret_cast<double*>(smraw + 128);
-    const int ldl = rowwise ? pitch4(chi_l) : chi_l, ldr = rowwise ? pitch4(chi_r) : chi_r;
+    // rows stay contiguous (one bulk copy per operand and stage): copying row by row into a padded, conflict-free
+    // pitch was measured slower (35 small copies per stage saturate the copy engine; the 2-way conflicts cost less)
+    const int ldl = chi_l, ldr = chi_r;
+    constexpr int LOOK = SR - 2;                                  // stages in flight ahead of the compute cursor
     const int stage_sz = KC * (ldl + ldr + 2 * d) + KC;           // L | R | xl | xr | w
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fc = lane & 3;
@@ -75,13 +74,8 @@ bond_grad_kr_kernel(const double* __restrict__ xl, const double* __restrict__ xr
         double* sw = sxr + KC * d;
         const int64_t i0 = ichunk * KC;
         // one row per lane: rows land with a pitch == 4 (mod 16) doubles -> conflict-free fragment loads
-        if (rowwise) {
-            if (lane < KC) bulk_g2s(sL + lane * ldl, L + (i0 + lane) * chi_l, (uint32_t)(chi_l * sizeof(double)), &raw_full[s]);
-            else bulk_g2s(sR + (lane - KC) * ldr, R + (i0 + lane - KC) * chi_r, (uint32_t)(chi_r * sizeof(double)), &raw_full[s]);
-        } else {
-            if (lane == 3) bulk_g2s(sL, L + i0 * chi_l, (uint32_t)(KC * chi_l * sizeof(double)), &raw_full[s]);
-            if (lane == 4) bulk_g2s(sR, R + i0 * chi_r, (uint32_t)(KC * chi_r * sizeof(double)), &raw_full[s]);
-        }
+        if (lane == 3) bulk_g2s(sL, L + i0 * chi_l, (uint32_t)(KC * chi_l * sizeof(double)), &raw_full[s]);
+        if (lane == 4) bulk_g2s(sR, R + i0 * chi_r, (uint32_t)(KC * chi_r * sizeof(double)), &raw_full[s]);
         if (lane == 0) bulk_g2s(sxl, xl + i0 * d, (uint32_t)(KC * d * sizeof(double)), &raw_full[s]);
         if (lane == 1) bulk_g2s(sxr, xr + i0 * d, (uint32_t)(KC * d * sizeof(double)), &raw_full[s]);
         if (lane == 2) bulk_g2s(sw, w + (int64_t)icls * wstride + i0, (uint32_t)(KC * sizeof(double)), &raw_full[s]);
@@ -284,9 +278,7 @@ int launch_kr(mpst_ctx* c, const double* xl, const double* xr, const double* L, 
     auto kern = bond_grad_kr_kernel<MA, S, NB, T, NW>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(c, MPST_T_GRADK);
-    const int rowwise = getenv("MPST_KR_ROW") ? atoi(getenv("MPST_KR_ROW")) : 0;   // measured: 35 small bulk copies per chunk cost more than the 2-way conflicts
-    const int look = std::max(1, std::min(SR - 2, getenv("MPST_KR_LOOK") ? atoi(getenv("MPST_KR_LOOK")) : SR - 2));
-    kern<<<ncta, 32 * NW, smem, c->stream>>>(xl, xr, L, R, c->w, c->Npad, d, chi_l, chi_r, geo, c->segs, c->cta_ptr, c->part, rowwise, look);
+    kern<<<ncta, 32 * NW, smem, c->stream>>>(xl, xr, L, R, c->w, c->Npad, d, chi_l, chi_r, geo, c->segs, c->cta_ptr, c->part);
     prof_end(c, MPST_T_GRADK);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
@@ -305,11 +297,10 @@ int launch_bond_grad_kr(mpst_ctx* c, const double* xl, const double* xr, const d
     *handled = false;
     if (getenv("MPST_GRAD_NOKR")) return MPST_OK;
     if ((chi_l & 1) || (chi_r & 1) || chi_l < 8 || chi_r < 8) return MPST_OK;       // 16-byte rows for the bulk copies
-    const size_t smem = 128 + sizeof(double) * (size_t)SR * (KC * (pitch4(chi_l) + pitch4(chi_r) + 2 * d) + KC);
+    const size_t smem = 128 + sizeof(double) * (size_t)SR * (KC * (chi_l + chi_r + 2 * d) + KC);
     if (smem > 227 * 1024) return MPST_OK;
     if (d % 6 == 0) {
         *handled = true;
-        if (getenv("MPST_KR_W16")) return launch_kr<1, 6, 1, 3, 16>(c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem);
         return launch_kr<1, 6, 1, 6, 8>(c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem);
     }
     if (d % 4 == 0) {
