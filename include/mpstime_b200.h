@@ -121,6 +121,15 @@ int mpst_bond_step(mpst_ctx* ctx, int lid, int going_left, const mpst_train_opts
 int mpst_sweep(mpst_ctx* ctx, const mpst_train_opts* opts, int nsweeps, double* per_bond_loss,
                double* per_bond_gradnorm, int32_t* per_bond_chi);
 
+/* ---- a block of `n_bonds` consecutive bond updates of the same (backward, forward) cycle that mpst_sweep runs,
+ *      continuing where the previous call stopped (restart != 0, or the first call after mpst_set_core /
+ *      mpst_train_load_*, rebuilds LE and starts at the right edge; the label index must then be on the last
+ *      site).  No normalize!(W) at the end: this is the sweep loop cut into pieces, for callers that interleave
+ *      logging / early exit with training (RealRealHighDimension.jl:726-850) and for bench.py's fixed-size steps
+ *      at the north-star shape.  Optional per-bond outputs have n_bonds entries. ------------------------------ */
+int mpst_sweep_bonds(mpst_ctx* ctx, const mpst_train_opts* opts, int n_bonds, int restart, double* per_bond_loss,
+                     double* per_bond_gradnorm, int32_t* per_bond_chi);
+
 /* ---- K7: contract_mps / classify / MSE_loss_acc (summary.jl:4-136).  X: T x n column-major in
  *      the encoding range (basis from the loaded training set) or phi (d x T x n) when the
  *      context was loaded with precomputed phi.  yhat: C x n column-major; argmax: n (0-based
@@ -166,6 +175,16 @@ int mpst_timer_start(mpst_ctx* ctx);
 int mpst_timer_stop(mpst_ctx* ctx, double* ms);
 int mpst_profile_reset(mpst_ctx* ctx);
 int64_t mpst_launch_count(mpst_ctx* ctx);
+
+/* ---- test / experiment switches.  The library reads MPST_<NAME> environment variables exactly once, in
+ *      mpst_create; afterwards a switch changes only through mpst_debug_set (name without the MPST_ prefix, case
+ *      insensitive: "NO_ENV_REUSE", "SVD_NOSUB", "SVD_NOHALF", "GRAD_NOKR", "KRAO_NOREG", "DENSE_FWD", ...).
+ *      mpst_debug_get returns a switch, or which code path the last call took: "svd_path" (1 tall-Gram, 2 wide-Gram,
+ *      3 subspace iteration, 4 fused Jacobi, 5 three-kernel Jacobi), "svd_iters", "svd_restarts", "grad_kernel"
+ *      (1 register-operand, 2 shared-memory tiles), "grad_variant", "krao_kernel" (1 register-operand, 2 tiles),
+ *      "krao_variant", "fwd_path" (1 factorised + cached environment, 2 factorised, 3 dense); -1 = unknown name. */
+int mpst_debug_set(mpst_ctx* ctx, const char* name, int value);
+int64_t mpst_debug_get(mpst_ctx* ctx, const char* name);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,7 @@ SIGNATURES = {
     "mpst_bond_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(TrainOpts), c_double_p, c_double_p,
                                  c_i32_p]),
     "mpst_sweep": (C.c_int, [C.c_void_p, C.POINTER(TrainOpts), C.c_int, c_double_p, c_double_p, c_i32_p]),
+    "mpst_sweep_bonds": (C.c_int, [C.c_void_p, C.POINTER(TrainOpts), C.c_int, C.c_int, c_double_p, c_double_p, c_i32_p]),
     "mpst_overlaps": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_i64_p]),
     "mpst_impute_batch": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_u8_p, C.c_int64, C.c_int, c_double_p,
                                     C.c_int, c_double_p, C.c_int, C.c_double, c_double_p]),
@@ -54,6 +55,8 @@ SIGNATURES = {
     "mpst_timer_stop": (C.c_int, [C.c_void_p, c_double_p]),
     "mpst_profile_reset": (C.c_int, [C.c_void_p]),
     "mpst_launch_count": (C.c_int64, [C.c_void_p]),
+    "mpst_debug_set": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "mpst_debug_get": (C.c_int64, [C.c_void_p, C.c_char_p]),
 }
 
 _lib = None

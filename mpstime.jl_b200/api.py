@@ -66,6 +66,19 @@ class MPSOptions:
             raise ValueError("loss_grad must be :KLD or :MSE on the array path")
         if self.use_legacy_ITensor:
             raise ValueError("use_legacy_ITensor=true selects the reference's own ITensor trainer; not this backend")
+        # options that change the reference's results and that the device path does not implement are refused,
+        # never silently ignored
+        if self.projected_basis:
+            raise ValueError("projected_basis=true is not implemented by the B200 backend")
+        if self.encode_classes_separately:
+            raise ValueError("encode_classes_separately=true only affects data-driven bases (Encodings/encodings.jl:112-131), "
+                             "which the B200 backend takes as precomputed phi (mpst_train_load_phi)")
+        if np.dtype(self.dtype) != np.dtype(np.float64):
+            raise ValueError(f"dtype {self.dtype!r}: the array training path is Float64-only (loss_functions.jl:343)")
+        if str(self.svd_alg).lstrip(":") not in ("divide_and_conquer", "qr_iteration", "recursive"):
+            raise ValueError(f"unknown svd_alg {self.svd_alg!r}")
+        # svd_alg picks the LAPACK driver in the reference; every choice yields the same truncated factors up to
+        # rounding, and the device SVD (K5) replaces all of them
         return _ENC[enc]
 
 

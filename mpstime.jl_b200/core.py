@@ -176,6 +176,18 @@ class Context:
         self._chk(self.lib.mpst_sweep(self.h, C.byref(opts), int(nsweeps), None, None, None))
         return None
 
+    def sweep_bonds(self, opts, n_bonds, restart=False, record=True):
+        """`n_bonds` consecutive bond updates of the sweep cycle, continuing where the last call stopped."""
+        if record:
+            lo = np.zeros(n_bonds)
+            gn = np.zeros(n_bonds)
+            chi = np.zeros(n_bonds, dtype=np.int32)
+            self._chk(self.lib.mpst_sweep_bonds(self.h, C.byref(opts), int(n_bonds), int(bool(restart)), _dp(lo), _dp(gn),
+                                                chi.ctypes.data_as(c_i32_p)))
+            return lo, gn, chi
+        self._chk(self.lib.mpst_sweep_bonds(self.h, C.byref(opts), int(n_bonds), int(bool(restart)), None, None, None))
+        return None
+
     # ---- K7 ---------------------------------------------------------------------------------
     def overlaps(self, X_TxN=None, phi_NTd=None):
         """returns (yhat (n, C), argmax (n,) 0-based class index)."""
@@ -264,6 +276,12 @@ class Context:
         wk = np.zeros(len(TIMER_NAMES))
         self._chk(self.lib.mpst_profile_get(self.h, _dp(ms), n.ctypes.data_as(c_i64_p), _dp(wk)))
         return {k: (float(ms[i]), int(n[i]), float(wk[i])) for i, k in enumerate(TIMER_NAMES)}
+
+    def debug_set(self, name, value):
+        self._chk(self.lib.mpst_debug_set(self.h, name.encode(), int(value)))
+
+    def debug_get(self, name):
+        return int(self.lib.mpst_debug_get(self.h, name.encode()))
 
     def timer_start(self):
         self._chk(self.lib.mpst_timer_start(self.h))

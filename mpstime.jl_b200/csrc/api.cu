@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <strings.h>
 #include "mpst_common.cuh"
 
 // ---- kernel launchers defined in the other translation units ---------------------------------
@@ -159,6 +160,60 @@ static int reserve(mpst_ctx* c, double*& p, size_t& cap, size_t need) {
     return MPST_OK;
 }
 
+// ---- stream-K schedule cache ---------------------------------------------------------------------
+SegTable* segtable_find(mpst_ctx* c, const std::vector<int64_t>& key) {
+    for (auto& t : c->segtabs)
+        if (t.key == key) { t.last_use = ++c->seg_clock; return &t; }
+    return nullptr;
+}
+
+int segtable_add(mpst_ctx* c, const std::vector<int64_t>& key, const std::vector<GradSeg>& segs,
+                 const std::vector<int>& cta_ptr, const std::vector<int>& tile_slot, SegTable** out) {
+    if (c->segtabs.size() >= 32) {                                 // evict the least recently used schedule
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        size_t lru = 0;
+        for (size_t i = 1; i < c->segtabs.size(); i++) if (c->segtabs[i].last_use < c->segtabs[lru].last_use) lru = i;
+        cudaFree(c->segtabs[lru].segs); cudaFree(c->segtabs[lru].cta_ptr); cudaFree(c->segtabs[lru].tile_slot);
+        c->segtabs.erase(c->segtabs.begin() + lru);
+    }
+    SegTable t;
+    t.key = key;
+    t.nseg = (int)segs.size();
+    t.last_use = ++c->seg_clock;
+    CUDA_TRY(c, cudaMalloc(&t.segs, std::max<size_t>(1, segs.size()) * sizeof(GradSeg)));
+    CUDA_TRY(c, cudaMalloc(&t.cta_ptr, cta_ptr.size() * sizeof(int)));
+    CUDA_TRY(c, cudaMalloc(&t.tile_slot, tile_slot.size() * sizeof(int)));
+    CUDA_TRY(c, cudaMemcpyAsync(t.segs, segs.data(), segs.size() * sizeof(GradSeg), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(t.cta_ptr, cta_ptr.data(), cta_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(t.tile_slot, tile_slot.data(), tile_slot.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));                 // the host vectors die with the caller (first use of a shape only)
+    c->segtabs.push_back(t);
+    *out = &c->segtabs.back();
+    return MPST_OK;
+}
+
+// ---- run-time switches: environment read once at mpst_create, mpst_debug_set afterwards -----------
+namespace {
+struct FlagDef { const char* name; int def; bool presence; };
+const FlagDef kFlags[F_COUNT] = {
+    {"DENSE_FWD", 0, true}, {"NO_ENV_REUSE", 0, true}, {"GRAD_T128", 0, true}, {"GRAD_NOKR", 0, true},
+    {"IMPUTE_NODBUF", 0, true}, {"IMPUTE_DEBUG", 0, true}, {"KRAO_NOREG", 0, true}, {"SVD_INNER", 1, false},
+    {"SVD_DEBUG", 0, true}, {"SVD_SKIP", 0, false}, {"SVD_FIXED", 0, false}, {"SVD_FULL", 0, true},
+    {"SVD_PB64", 0, true}, {"SVD_LEGACY", 0, true}, {"SVD_NOSUB", 0, true}, {"SVD_OVS", 0, false},
+    {"SVD_NOHALF", 0, true}, {"SVD_HALF_FROM", 1, false}, {"SVD_IT", 0, false}, {"SVD_NOGRAPH", 0, true},
+    {"GRAD_KC", 0, false},
+};
+const char* kLast[L_COUNT] = {"svd_path", "svd_iters", "svd_restarts", "grad_kernel", "grad_variant", "krao_kernel",
+                              "krao_variant", "fwd_path", "krao_reg_mask"};
+void flags_from_env(mpst_ctx* c) {
+    for (int f = 0; f < F_COUNT; f++) {
+        c->flag[f] = kFlags[f].def;
+        const std::string var = std::string("MPST_") + kFlags[f].name;
+        if (const char* v = getenv(var.c_str())) c->flag[f] = kFlags[f].presence ? 1 : atoi(v);
+    }
+}
+}  // namespace
+
 // ---- NCCL through dlopen (no link-time dependency; prefers the copy already in the process) ---
 namespace {
 struct NcclId { char internal[128]; };
@@ -202,6 +257,8 @@ extern "C" {
 
 int mpst_version(void) { return 100; }
 
+int mpst_destroy(mpst_ctx* c);
+
 int mpst_create(mpst_ctx** out, int device_id) {
     if (!out) return MPST_E_INVALID;
     *out = nullptr;
@@ -215,17 +272,23 @@ int mpst_create(mpst_ctx** out, int device_id) {
     cudaGetDeviceProperties(&prop, device_id);
     if (prop.major < 10) { delete c; return MPST_E_UNSUPPORTED; }               // sm_100a only
     c->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MPST_E_CUDA; }
-    cudaMalloc(&c->scal, 32 * sizeof(double));
-    cudaMemset(c->scal, 0, 32 * sizeof(double));
-    cudaMallocHost(&c->hscal, 32 * sizeof(double));
-    cudaMalloc(&c->meta, 256 * sizeof(double));
-    cudaMallocHost(&c->hmeta, 256 * sizeof(double));
-    cudaMalloc(&c->iscal, 16 * sizeof(int));
-    cudaMallocHost(&c->hiscal, 16 * sizeof(int));
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { c->stream = nullptr; delete c; return MPST_E_CUDA; }
     const size_t maxn = (size_t)MPST_MAX_D * MPST_MAX_CHI + 64;
-    cudaMalloc(&c->colnorm, 2 * maxn * sizeof(double));
-    cudaMalloc(&c->perm, maxn * sizeof(int));
+    bool ok = cudaMalloc(&c->scal, 32 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMemset(c->scal, 0, 32 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->hscal, 32 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->meta, 256 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->hmeta, 256 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->iscal, 16 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMemset(c->iscal, 0, 16 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->hiscal, 16 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->colnorm, 2 * maxn * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->perm, maxn * sizeof(int)) == cudaSuccess;
+    if (!ok) { mpst_destroy(c); return MPST_E_CUDA; }
+    for (int k = 0; k < 32; k++) c->hscal[k] = 0.0;
+    for (int k = 0; k < 16; k++) c->hiscal[k] = 0;
+    c->nonfinite = c->iscal + 1;                                   // read back together with chi_new (iscal[0])
+    flags_from_env(c);
     *out = c;
     return MPST_OK;
 }
@@ -233,9 +296,12 @@ int mpst_create(mpst_ctx** out, int device_id) {
 int mpst_destroy(mpst_ctx* c) {
     if (!c) return MPST_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     prof_drain(c);
     for (auto e : c->evpool) cudaEventDestroy(e);
+    if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
+    for (auto& t : c->segtabs) { cudaFree(t.segs); cudaFree(t.cta_ptr); cudaFree(t.tile_slot); }
+    c->segtabs.clear();
     free_training(c, true);
     auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(c->B); fr(c->G); fr(c->Z); fr(c->part); fr(c->red); fr(c->scal); fr(c->S); fr(c->gpart); fr(c->wbuf);
@@ -247,10 +313,8 @@ int mpst_destroy(mpst_ctx* c) {
     if (c->iscal) cudaFree(c->iscal);
     if (c->hscal) cudaFreeHost(c->hscal);
     if (c->hiscal) cudaFreeHost(c->hiscal);
-    if (c->segs) { cudaFree(c->segs); cudaFree(c->cta_ptr); cudaFree(c->tile_slot); }
-    if (c->hsegs) { cudaFreeHost(c->hsegs); cudaFreeHost(c->hcta_ptr); cudaFreeHost(c->htile_slot); }
     if (c->nccl_comm && g_nccl.destroy) g_nccl.destroy(c->nccl_comm);
-    cudaStreamDestroy(c->stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return MPST_OK;
 }
@@ -268,6 +332,11 @@ int mpst_comm_unique_id(void* id128) {
 
 int mpst_comm_init(mpst_ctx* c, const void* id128, int rank, int world) {
     if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return MPST_E_INVALID;
+    if (c->nccl_comm) {                                            // a second fitMPS call on the same context
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        if (g_nccl.destroy) g_nccl.destroy(c->nccl_comm);
+        c->nccl_comm = nullptr;
+    }
     c->rank = rank;
     c->world = world;
     if (world == 1) return MPST_OK;
@@ -312,6 +381,7 @@ static int model_reset(mpst_ctx* c, int T, int C, int d, int chi_max) {
     c->env_chi.assign(T, 0);
     c->core_ver.assign(T, 0); c->env_ver.assign(T, 0); c->env_core_ver.assign(T, 0); c->env_src_ver.assign(T, 0);
     c->env_dir.assign(T, 0);
+    c->sw_cursor = -1;
     c->svd_its.clear();
     c->svd_floor.clear();
     c->svd_nohalf.clear();
@@ -422,6 +492,7 @@ int mpst_set_core(mpst_ctx* c, int site, const double* data, int chi_l, int chi_
     TRY(core_reserve(c, k, std::max(cap, n)));
     k.chi_l = chi_l; k.chi_r = chi_r; k.has_label = has_label ? 1 : 0; k.orient = ORIENT_LEFT;
     mark_core(c, site);
+    c->sw_cursor = -1;
     TRY(ensure_buf(c, &c->tmp, &c->tmpcap, n));
     CUDA_TRY(c, cudaMemcpyAsync(c->tmp, data, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     // wire: a + chi_l*(s + d*(b + chi_r*c))  ->  LEFT: s + d*(a + chi_l*b) + d*chi_l*chi_r*c
@@ -516,7 +587,8 @@ static int loss_grad_device(mpst_ctx* c, const double* phl, const double* phr, c
     // forward: yhat[c][i] = <B_c, phi~_i>
     {
         ProfScope ps(c, MPST_T_FWD);
-        if (fac_l && fac_r && !getenv("MPST_DENSE_FWD")) {
+        if (fac_l && fac_r && !c->flag[F_DENSE_FWD]) {
+            c->last[L_FWD_PATH] = cached_unlab ? 1 : 2;
             // factorised: a = P W_l (N x chi_m [per class if W_l carries the label]), b = Q W_r, yhat = a . b
             const int chi_m = fac_l->chi_r;
             const bool lab_l = fac_l->has_label != 0;
@@ -539,6 +611,7 @@ static int loss_grad_device(mpst_ctx* c, const double* phl, const double* phr, c
             c->prof_work[MPST_T_FWD] -= 2.0 * (loss_kind == MPST_LOSS_KLD ? (double)c->N : (double)c->N * C) * (double)D;
             c->prof_work[MPST_T_FWD] += 2.0 * (double)c->N * chi_m * ((double)(lab_l ? Dr : Dl) + (double)(lab_l ? Dl : Dr) * (loss_kind == MPST_LOSS_KLD ? 1 : C));
         } else {
+        c->last[L_FWD_PATH] = 3;
         // dense: Z = P * B_c in row blocks, then the Q-weighted row sum
         const int64_t SB = std::max<int64_t>(MPST_TILE, ((int64_t)(96 << 20) / (8 * (int64_t)Dr)) / MPST_TILE * MPST_TILE);
         TRY(ensure_buf(c, &c->Z, &c->Zcap, (size_t)(SB + 2 * MPST_TILE) * Dr));
@@ -611,8 +684,11 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
     if (kl.has_label + kr.has_label != 1) { c->err = "bond_step: the label index must be on one of the two bond sites"; return MPST_E_INVALID; }
     if (kl.chi_r != kr.chi_l) { c->err = "bond_step: link dimension mismatch"; return MPST_E_INVALID; }
     const int chi_l = kl.chi_l, chi_m = kl.chi_r, chi_r = kr.chi_r;
-    if (l > 0 && c->env_chi[l - 1] != chi_l) { c->err = "bond_step: left environment missing/stale"; return MPST_E_INVALID; }
-    if (r < T - 1 && c->env_chi[r + 1] != chi_r) { c->err = "bond_step: right environment missing/stale"; return MPST_E_INVALID; }
+    // the slot ring is shared by LE and RE: besides the link dimension the slot must hold an environment of the right
+    // direction computed from the current cores (set_core on a neighbour, a wrong going_left or an out-of-order call
+    // would otherwise contract a stale or mirrored environment whenever the dimensions happen to match)
+    if (l > 0 && (c->env_chi[l - 1] != chi_l || !env_fresh(c, l - 1, 1))) { c->err = "bond_step: left environment missing/stale (call mpst_build_env)"; return MPST_E_INVALID; }
+    if (r < T - 1 && (c->env_chi[r + 1] != chi_r || !env_fresh(c, r + 1, 2))) { c->err = "bond_step: right environment missing/stale (call mpst_build_env)"; return MPST_E_INVALID; }
     const int Dl = d * chi_l, Dr = d * chi_r;
     const size_t D = (size_t)Dl * Dr;
     if (D * C + 64 > c->Dcap) {
@@ -623,6 +699,7 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         CUDA_TRY(c, cudaMalloc(&c->B, c->Dcap * sizeof(double)));
         CUDA_TRY(c, cudaMalloc(&c->G, c->Dcap * sizeof(double)));
     }
+    CUDA_TRY(c, cudaMemsetAsync(c->nonfinite, 0, sizeof(int), c->stream));
     const double *phl, *phr;
     TRY(site_phi(c, l, c->phi_l, &phl));
     TRY(site_phi(c, r, c->phi_r, &phr));
@@ -652,7 +729,7 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         // The unlabelled forward factor P W_l (resp. Q W_r) is the environment of that site; when the slot still holds
         // it -- computed from this very core and neighbour slot by the previous sweep direction -- the GEMM is skipped.
         const double* cached = nullptr;
-        if (factored && !getenv("MPST_NO_ENV_REUSE")) {
+        if (factored && !c->flag[F_NO_ENV_REUSE]) {
             const int u = kl.has_label ? r : l, dir = kl.has_label ? 2 : 1;
             if (env_fresh(c, u, dir) && c->env_chi[u] == chi_m) cached = slot_ptr(c, u);
         }
@@ -693,6 +770,19 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         const int rc_svd = svd_split_device(c, c->B, Dl, Dr, C, going_left, o->chi_max, o->cutoff, norm2_dev, klabel.dev,
                                             kortho.dev, &chi_new, nullptr, nullptr);
         c->svd_slot = -1;
+        // every SVD path ends with one D2H copy of {chi_new, non-finite flag} + a stream sync: the flag is checked on
+        // every bond and every optimiser iteration, whether or not the caller asked for the loss
+        if (rc_svd != MPST_OK) {
+            cudaMemcpyAsync(c->hiscal + 1, c->nonfinite, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+            cudaStreamSynchronize(c->stream);
+        }
+        if (c->hiscal[1]) {
+            char b[160];
+            snprintf(b, sizeof b, "bond_step: non-finite loss or gradient at bond (%d,%d) (an overlap hit zero?)", l, r);
+            c->err = b;
+            c->hiscal[1] = 0;
+            return MPST_E_NUMERIC;
+        }
         TRY(rc_svd);
         mark_core(c, l);
         mark_core(c, r);
@@ -723,6 +813,7 @@ int mpst_sweep(mpst_ctx* c, const mpst_train_opts* o, int nsweeps, double* per_b
     if (!c || !o || c->T == 0 || nsweeps < 0) return MPST_E_INVALID;
     const int T = c->T;
     if (!c->cores[T - 1].dev || !c->cores[T - 1].has_label) { c->err = "sweep: the label index must start on the last site"; return MPST_E_INVALID; }
+    c->sw_cursor = -1;
     TRY(mpst_build_env(c, 1));                                        // :631
     size_t idx = 0;
     for (int it = 0; it < nsweeps; it++) {
@@ -759,6 +850,50 @@ int mpst_sweep(mpst_ctx* c, const mpst_train_opts* o, int nsweeps, double* per_b
     }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return MPST_OK;
+}
+
+int mpst_sweep_bonds(mpst_ctx* c, const mpst_train_opts* o, int n_bonds, int restart, double* per_bond_loss,
+                     double* per_bond_gradnorm, int32_t* per_bond_chi) {
+    if (!c || !o || c->T == 0 || n_bonds < 0) return MPST_E_INVALID;
+    const int T = c->T, cycle = 2 * (T - 1);
+    if (restart || c->sw_cursor < 0) {
+        if (!c->cores[T - 1].dev || !c->cores[T - 1].has_label) { c->err = "sweep_bonds: the label index must start on the last site"; return MPST_E_INVALID; }
+        TRY(mpst_build_env(c, 1));
+        c->sw_cursor = 0;
+    }
+    const bool want = per_bond_loss || per_bond_gradnorm;
+    for (int k = 0; k < n_bonds; k++) {
+        const int cur = c->sw_cursor;
+        const bool left = cur < T - 1;
+        const int j = left ? T - 2 - cur : cur - (T - 1);
+        double lo = 0, gn = 0;
+        int chi = 0;
+        const int rc = mpst_bond_step(c, j, left, o, want ? &lo : nullptr, want ? &gn : nullptr, &chi);
+        if (rc != MPST_OK) { c->sw_cursor = -1; return rc; }
+        if (per_bond_loss) per_bond_loss[k] = lo;
+        if (per_bond_gradnorm) per_bond_gradnorm[k] = gn;
+        if (per_bond_chi) per_bond_chi[k] = chi;
+        c->sw_cursor = (cur + 1) % cycle;
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MPST_OK;
+}
+
+int mpst_debug_set(mpst_ctx* c, const char* name, int value) {
+    if (!c || !name) return MPST_E_INVALID;
+    for (int f = 0; f < F_COUNT; f++)
+        if (strcasecmp(name, kFlags[f].name) == 0) { c->flag[f] = value; return MPST_OK; }
+    for (int k = 0; k < L_COUNT; k++)
+        if (strcasecmp(name, kLast[k]) == 0) { c->last[k] = value; return MPST_OK; }
+    c->err = std::string("debug_set: unknown switch ") + name;
+    return MPST_E_INVALID;
+}
+
+int64_t mpst_debug_get(mpst_ctx* c, const char* name) {
+    if (!c || !name) return -1;
+    for (int k = 0; k < L_COUNT; k++) if (strcasecmp(name, kLast[k]) == 0) return c->last[k];
+    for (int f = 0; f < F_COUNT; f++) if (strcasecmp(name, kFlags[f].name) == 0) return c->flag[f];
+    return -1;
 }
 
 int mpst_overlaps(mpst_ctx* c, const double* X_or_phi, int64_t n, double* yhat, int64_t* argmax) {

@@ -15,7 +15,9 @@
 // sums the segments of each tile in a fixed order (deterministic, no atomics).
 // Per chunk the raw factors arrive by 1-D bulk TMA (rows of 16 consecutive samples are contiguous)
 // on a 2-stage mbarrier ring; the 128x16 / 16x128 operand tiles are double buffered.
+#include <algorithm>
 #include <cstdlib>
+#include <vector>
 #include "mpst_common.cuh"
 #include "dmma.cuh"
 
@@ -226,7 +228,7 @@ int launch_bond_grad(mpst_ctx* c, const double* xl, const double* xr, const doub
     // tile shapes: 128 x 128 by default; 160 x 96 when that removes the padding (d*chi = 480 at config B:
     // 3 x 5 exact tiles instead of 4 x 4 tiles of which 12 % is padding)
     int TP = 128, TQ = 128;
-    if (!getenv("MPST_GRAD_T128")) {
+    if (!c->flag[F_GRAD_T128]) {
         const double w128 = (double)((Dl + 127) / 128 * 128) * ((Dr + 127) / 128 * 128);
         const double w160 = (double)((Dl + 159) / 160 * 160) * ((Dr + 95) / 96 * 96);
         if (w160 < 0.95 * w128) { TP = 160; TQ = 96; }
@@ -240,65 +242,55 @@ int launch_bond_grad(mpst_ctx* c, const double* xl, const double* xr, const doub
     // chunk size: 32 samples per pipeline step when the staging buffers fit in shared memory, else 16
     const int LDT = std::max(TP, TQ) + 4;
     const size_t smem32 = 16 + sizeof(double) * (2 * (size_t)32 * (chi_l + chi_r + 2 * d + 1) + 4 * (size_t)32 * LDT);
-    const int KC = (smem32 <= 227 * 1024 && getenv("MPST_GRAD_KC32")) ? 32 : 16;   // measured: 16 is faster (24.5 vs 23.8 TFLOP/s)
+    const int KC = (smem32 <= 227 * 1024 && c->flag[F_GRAD_KC] == 32) ? 32 : 16;   // measured: 16 is faster (24.5 vs 23.8 TFLOP/s)
     for (int k = 0; k < ncls; k++) {
         cb[k] = cls_begin[k] / KC;
         ce[k] = (cls_end[k] + KC - 1) / KC;
         if (cls_end[k] <= cls_begin[k]) ce[k] = cb[k];
         total += (ce[k] - cb[k]) * ntp * ntq;
     }
-    const size_t max_segs = (size_t)ntiles + ncta + 2;
-    if (max_segs > c->segcap) {
-        if (c->segs) { cudaFree(c->segs); cudaFree(c->cta_ptr); cudaFree(c->tile_slot); }
-        if (c->hsegs) { cudaFreeHost(c->hsegs); cudaFreeHost(c->hcta_ptr); cudaFreeHost(c->htile_slot); }
-        c->segcap = max_segs * 2;
-        CUDA_TRY(c, cudaMalloc(&c->segs, c->segcap * sizeof(GradSeg)));
-        CUDA_TRY(c, cudaMalloc(&c->cta_ptr, (ncta + 1) * sizeof(int)));
-        CUDA_TRY(c, cudaMalloc(&c->tile_slot, (c->segcap + 1) * sizeof(int)));
-        CUDA_TRY(c, cudaMallocHost(&c->hsegs, c->segcap * sizeof(GradSeg)));
-        CUDA_TRY(c, cudaMallocHost(&c->hcta_ptr, (ncta + 1) * sizeof(int)));
-        CUDA_TRY(c, cudaMallocHost(&c->htile_slot, (c->segcap + 1) * sizeof(int)));
-    }
-    // the pinned tables may still be in flight from the previous bond
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    int nseg = 0;
     if (total == 0) {
         CUDA_TRY(c, cudaMemsetAsync(G, 0, sizeof(double) * (size_t)ncls * Dl * Dr, c->stream));
         return MPST_OK;
     }
-    // linear work space: tile-major, chunks within the tile
-    int64_t pos = 0;      // global chunk cursor
-    int cta = 0;
-    int64_t cta_end = (total * (cta + 1)) / ncta;
-    c->hcta_ptr[0] = 0;
-    for (int tile = 0; tile < ntiles; tile++) {
-        const int cls = tile / (ntp * ntq);
-        const int rem = tile - cls * ntp * ntq;
-        const int tp = rem / ntq, tq = rem - tp * ntq;
-        c->htile_slot[tile] = nseg;
-        int64_t j = cb[cls];
-        while (j < ce[cls]) {
-            while (pos >= cta_end && cta < ncta - 1) {           // advance to the CTA owning `pos`
-                cta++;
-                c->hcta_ptr[cta] = nseg;
-                cta_end = (total * (cta + 1)) / ncta;
+    // The schedule depends only on (tile shape, tile counts, class chunk ranges): built once, kept on the device
+    std::vector<int64_t> key = {2, TP, TQ, KC, ncta, ntp, ntq, ncls};
+    for (int k = 0; k < ncls; k++) { key.push_back(cb[k]); key.push_back(ce[k]); }
+    SegTable* tab = segtable_find(c, key);
+    if (!tab) {
+        std::vector<GradSeg> hsegs;
+        std::vector<int> hcta(ncta + 1, 0), hslot(ntiles + 1, 0);
+        // linear work space: tile-major, chunks within the tile
+        int64_t pos = 0;      // global chunk cursor
+        int cta = 0;
+        int64_t cta_end = (total * (cta + 1)) / ncta;
+        for (int tile = 0; tile < ntiles; tile++) {
+            const int cls = tile / (ntp * ntq);
+            const int rem = tile - cls * ntp * ntq;
+            const int tp = rem / ntq, tq = rem - tp * ntq;
+            hslot[tile] = (int)hsegs.size();
+            int64_t j = cb[cls];
+            while (j < ce[cls]) {
+                while (pos >= cta_end && cta < ncta - 1) {           // advance to the CTA owning `pos`
+                    cta++;
+                    hcta[cta] = (int)hsegs.size();
+                    cta_end = (total * (cta + 1)) / ncta;
+                }
+                const int64_t take = std::min<int64_t>(ce[cls] - j, cta_end - pos);
+                GradSeg sgm;
+                sgm.cls = cls; sgm.tp = tp; sgm.tq = tq; sgm.slot = (int)hsegs.size();
+                sgm.chunk_begin = j; sgm.chunk_end = j + take;
+                hsegs.push_back(sgm);
+                j += take;
+                pos += take;
             }
-            const int64_t take = std::min<int64_t>(ce[cls] - j, cta_end - pos);
-            GradSeg sgm;
-            sgm.cls = cls; sgm.tp = tp; sgm.tq = tq; sgm.slot = nseg;
-            sgm.chunk_begin = j; sgm.chunk_end = j + take;
-            c->hsegs[nseg++] = sgm;
-            j += take;
-            pos += take;
         }
+        hslot[ntiles] = (int)hsegs.size();
+        while (cta < ncta) { cta++; hcta[cta] = (int)hsegs.size(); }
+        TRY(segtable_add(c, key, hsegs, hcta, hslot, &tab));
     }
-    c->htile_slot[ntiles] = nseg;
-    while (cta < ncta) { cta++; c->hcta_ptr[cta] = nseg; }
-    const size_t need_part = (size_t)nseg * TP * TQ;
-    TRY(ensure_buf(c, &c->part, &c->partcap, need_part));
-    CUDA_TRY(c, cudaMemcpyAsync(c->segs, c->hsegs, nseg * sizeof(GradSeg), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(c->cta_ptr, c->hcta_ptr, (ncta + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(c->tile_slot, c->htile_slot, (ntiles + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    const int nseg = tab->nseg;
+    TRY(ensure_buf(c, &c->part, &c->partcap, (size_t)nseg * TP * TQ));
 
     const size_t smem = 16 + sizeof(double) * (2 * (size_t)KC * (chi_l + chi_r + 2 * d + 1) + 4 * (size_t)KC * LDT);
     void (*kern)(const double*, const double*, const double*, const double*, const double*, int64_t, int, int, int,
@@ -306,12 +298,14 @@ int launch_bond_grad(mpst_ctx* c, const double* xl, const double* xr, const doub
     if (KC == 32) kern = TP == 128 ? bond_grad_kernel<32, 4, 8> : bond_grad_kernel<32, 5, 6>;
     else kern = TP == 128 ? bond_grad_kernel<16, 4, 8> : bond_grad_kernel<16, 5, 6>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    c->last[L_GRAD_KERNEL] = 2;
+    c->last[L_GRAD_VARIANT] = TP * 1000 + TQ;
     prof_begin(c, MPST_T_GRADK);
-    kern<<<ncta, 256, smem, c->stream>>>(xl, xr, L, R, c->w, c->Npad, d, chi_l, chi_r, c->segs, c->cta_ptr, c->part);
+    kern<<<ncta, 256, smem, c->stream>>>(xl, xr, L, R, c->w, c->Npad, d, chi_l, chi_r, tab->segs, tab->cta_ptr, c->part);
     prof_end(c, MPST_T_GRADK);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
-    grad_reduce_kernel<<<ntiles, 256, 0, c->stream>>>(c->part, c->tile_slot, ntp, ntq, Dl, Dr, TP, TQ, G);
+    grad_reduce_kernel<<<ntiles, 256, 0, c->stream>>>(c->part, tab->tile_slot, ntp, ntq, Dl, Dr, TP, TQ, G);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
     return MPST_OK;

@@ -229,60 +229,55 @@ int launch_kr(mpst_ctx* c, const double* xl, const double* xr, const double* L, 
         if (cls_end[k] <= cls_begin[k]) ce[k] = cb[k];
         total += (ce[k] - cb[k]) * geo.ngroups;
     }
-    const size_t max_segs = (size_t)ngrp_total + ncta + 2;
-    if (max_segs > c->segcap) {
-        if (c->segs) { cudaFree(c->segs); cudaFree(c->cta_ptr); cudaFree(c->tile_slot); }
-        if (c->hsegs) { cudaFreeHost(c->hsegs); cudaFreeHost(c->hcta_ptr); cudaFreeHost(c->htile_slot); }
-        c->segcap = max_segs * 2;
-        CUDA_TRY(c, cudaMalloc(&c->segs, c->segcap * sizeof(GradSeg)));
-        CUDA_TRY(c, cudaMalloc(&c->cta_ptr, (ncta + 1) * sizeof(int)));
-        CUDA_TRY(c, cudaMalloc(&c->tile_slot, (c->segcap + 1) * sizeof(int)));
-        CUDA_TRY(c, cudaMallocHost(&c->hsegs, c->segcap * sizeof(GradSeg)));
-        CUDA_TRY(c, cudaMallocHost(&c->hcta_ptr, (ncta + 1) * sizeof(int)));
-        CUDA_TRY(c, cudaMallocHost(&c->htile_slot, (c->segcap + 1) * sizeof(int)));
-    }
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));                 // the pinned tables may still be in flight
     if (total == 0) {
         CUDA_TRY(c, cudaMemsetAsync(G, 0, sizeof(double) * (size_t)ncls * d * chi_l * d * chi_r, c->stream));
         return MPST_OK;
     }
-    int nseg = 0, cta = 0;
-    int64_t pos = 0, cta_end = total / ncta;
-    c->hcta_ptr[0] = 0;
-    for (int grp = 0; grp < ngrp_total; grp++) {
-        const int cls = grp / geo.ngroups, group = grp - cls * geo.ngroups;
-        c->htile_slot[grp] = nseg;
-        int64_t j = cb[cls];
-        while (j < ce[cls]) {
-            while (pos >= cta_end && cta < ncta - 1) {
-                cta++;
-                c->hcta_ptr[cta] = nseg;
-                cta_end = (total * (cta + 1)) / ncta;
+    // The schedule depends only on (kernel variant, group count, class chunk ranges): built once, kept on the device
+    std::vector<int64_t> key = {1, MA, S, NB, T, NW, KC, ncta, geo.ngroups, ncls};
+    for (int k = 0; k < ncls; k++) { key.push_back(cb[k]); key.push_back(ce[k]); }
+    SegTable* tab = segtable_find(c, key);
+    if (!tab) {
+        std::vector<GradSeg> hsegs;
+        std::vector<int> hcta(ncta + 1, 0), hslot(ngrp_total + 1, 0);
+        int cta = 0;
+        int64_t pos = 0, cta_end = total / ncta;
+        for (int grp = 0; grp < ngrp_total; grp++) {
+            const int cls = grp / geo.ngroups, group = grp - cls * geo.ngroups;
+            hslot[grp] = (int)hsegs.size();
+            int64_t j = cb[cls];
+            while (j < ce[cls]) {
+                while (pos >= cta_end && cta < ncta - 1) {
+                    cta++;
+                    hcta[cta] = (int)hsegs.size();
+                    cta_end = (total * (cta + 1)) / ncta;
+                }
+                const int64_t take = std::min<int64_t>(ce[cls] - j, cta_end - pos);
+                GradSeg sgm;
+                sgm.cls = cls; sgm.tp = group; sgm.tq = 0; sgm.slot = (int)hsegs.size();
+                sgm.chunk_begin = j; sgm.chunk_end = j + take;
+                hsegs.push_back(sgm);
+                j += take;
+                pos += take;
             }
-            const int64_t take = std::min<int64_t>(ce[cls] - j, cta_end - pos);
-            GradSeg sgm;
-            sgm.cls = cls; sgm.tp = group; sgm.tq = 0; sgm.slot = nseg;
-            sgm.chunk_begin = j; sgm.chunk_end = j + take;
-            c->hsegs[nseg++] = sgm;
-            j += take;
-            pos += take;
         }
+        hslot[ngrp_total] = (int)hsegs.size();
+        while (cta < ncta) { cta++; hcta[cta] = (int)hsegs.size(); }
+        TRY(segtable_add(c, key, hsegs, hcta, hslot, &tab));
     }
-    c->htile_slot[ngrp_total] = nseg;
-    while (cta < ncta) { cta++; c->hcta_ptr[cta] = nseg; }
+    const int nseg = tab->nseg;
     constexpr int RU = MA * S * 8, CU = NB * T * 8;
     TRY(ensure_buf(c, &c->part, &c->partcap, (size_t)nseg * NW * RU * CU));
-    CUDA_TRY(c, cudaMemcpyAsync(c->segs, c->hsegs, nseg * sizeof(GradSeg), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(c->cta_ptr, c->hcta_ptr, (ncta + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(c->tile_slot, c->htile_slot, (ngrp_total + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    c->last[L_GRAD_KERNEL] = 1;
+    c->last[L_GRAD_VARIANT] = MA * 1000 + S * 100 + KC;
     auto kern = bond_grad_kr_kernel<MA, S, NB, T, NW>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(c, MPST_T_GRADK);
-    kern<<<ncta, 32 * NW, smem, c->stream>>>(xl, xr, L, R, c->w, c->Npad, d, chi_l, chi_r, geo, c->segs, c->cta_ptr, c->part);
+    kern<<<ncta, 32 * NW, smem, c->stream>>>(xl, xr, L, R, c->w, c->Npad, d, chi_l, chi_r, geo, tab->segs, tab->cta_ptr, c->part);
     prof_end(c, MPST_T_GRADK);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
-    grad_kr_reduce_kernel<MA, S, NB, T, NW><<<dim3(ngrp_total, NW), 256, 0, c->stream>>>(c->part, c->tile_slot, geo, d, chi_l, chi_r, G);
+    grad_kr_reduce_kernel<MA, S, NB, T, NW><<<dim3(ngrp_total, NW), 256, 0, c->stream>>>(c->part, tab->tile_slot, geo, d, chi_l, chi_r, G);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
     return MPST_OK;
@@ -295,7 +290,7 @@ int launch_bond_grad_kr(mpst_ctx* c, const double* xl, const double* xr, const d
                         int chi_l, int chi_r, const int64_t* cls_begin, const int64_t* cls_end, int ncls, double* G,
                         bool* handled) {
     *handled = false;
-    if (getenv("MPST_GRAD_NOKR")) return MPST_OK;
+    if (c->flag[F_GRAD_NOKR]) return MPST_OK;
     if ((chi_l & 1) || (chi_r & 1) || chi_l < 8 || chi_r < 8) return MPST_OK;       // 16-byte rows for the bulk copies
     const size_t smem = 128 + sizeof(double) * (size_t)SR * (KC * (chi_l + chi_r + 2 * d) + KC);
     if (smem > 227 * 1024) return MPST_OK;

@@ -84,7 +84,7 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 __global__ void __launch_bounds__(256)
 loss_w_kernel(const double* __restrict__ yhat, double* __restrict__ w, int64_t N, int64_t Npad, int C,
               const int64_t* __restrict__ class_off, const double* __restrict__ denom, int loss_kind,
-              double* __restrict__ red) {
+              double* __restrict__ red, int* __restrict__ nonfinite) {
     __shared__ double sh[8];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double li = 0.0;
@@ -103,6 +103,8 @@ loss_w_kernel(const double* __restrict__ yhat, double* __restrict__ w, int64_t N
             }
         }
     }
+    // a zero / NaN overlap (KLD weight -1/(N yhat)) must not flow silently into the update and the SVD
+    if (!isfinite(li)) atomicOr(nonfinite, 1);
     const double s = block_sum(li, sh);
     if (threadIdx.x == 0) red[blockIdx.x] = s;
 }
@@ -120,12 +122,15 @@ sumsq_partial_kernel(const double* __restrict__ v, int64_t n, double* __restrict
 }
 
 __global__ void __launch_bounds__(256)
-final_sum_kernel(const double* __restrict__ red, int n, double* __restrict__ out) {
+final_sum_kernel(const double* __restrict__ red, int n, double* __restrict__ out, int* __restrict__ nonfinite) {
     __shared__ double sh[8];
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) s += red[i];
     s = block_sum(s, sh);
-    if (threadIdx.x == 0) *out = s;
+    if (threadIdx.x == 0) {
+        *out = s;
+        if (!isfinite(s)) atomicOr(nonfinite, 1);
+    }
 }
 
 // TSGO: B -= eta * G / ||G||   (loss_functions.jl:79);  GD: B -= eta * G   (:49)
@@ -238,7 +243,7 @@ int launch_rowdot(mpst_ctx* c, const double* A, int64_t lda, const double* Bm, i
 }
 
 int launch_final_sum(mpst_ctx* c, const double* red, int n, double* out_dev) {
-    final_sum_kernel<<<1, 256, 0, c->stream>>>(red, n, out_dev);
+    final_sum_kernel<<<1, 256, 0, c->stream>>>(red, n, out_dev, c->nonfinite);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
     return MPST_OK;
@@ -249,7 +254,7 @@ int launch_loss_w(mpst_ctx* c, int loss_kind, const int64_t* class_off_dev, cons
     const int blocks = (int)((c->N + 255) / 256);
     TRY(ensure_buf(c, &c->red, &c->redcap, (size_t)blocks + 4096));
     loss_w_kernel<<<blocks, 256, 0, c->stream>>>(c->yhat, c->w, c->N, c->Npad, c->C, class_off_dev, denom_dev,
-                                                loss_kind, c->red);
+                                                loss_kind, c->red, c->nonfinite);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
     return launch_final_sum(c, c->red, blocks, loss_out_dev);

@@ -659,7 +659,7 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     const int n8 = (chimax + 7) & ~7, ld = n8 + 4;
     size_t smem = sizeof(double) * ((size_t)4 * n8 * ld + 2 * n8 + 2 * (size_t)d * ld + 2 * (size_t)d * d + MPST_MAX_D + 32 +
                                     std::max(3 * NT + 16, 4 * n8) + MPST_MAX_D * MPST_MAX_D);
-    const bool dbuf = smem + sizeof(double) * (size_t)n8 * ld <= 227 * 1024 && !getenv("MPST_IMPUTE_NODBUF");
+    const bool dbuf = smem + sizeof(double) * (size_t)n8 * ld <= 227 * 1024 && !c->flag[F_IMPUTE_NODBUF];
     if (dbuf) smem += sizeof(double) * (size_t)n8 * ld;
     if (smem > 227 * 1024) { c->err = "impute_batch: chi too large for the shared-memory Gram matrices (chi <= 72 at d = 16)"; return MPST_E_UNSUPPORTED; }
     // host-side Kmax
@@ -718,7 +718,7 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     P.uniforms = dunif; P.out = dout; P.gr_scratch = dGR; P.p_scratch = dp;
     P.T = T; P.d = d; P.G = G; P.ntraj = n_traj; P.Kmax = Kmax; P.chimax = chimax; P.method = method; P.basis = c->basis;
     P.n = n; P.max_jump = max_jump;
-    P.debug = getenv("MPST_IMPUTE_DEBUG") ? 1 : 0;
+    P.debug = c->flag[F_IMPUTE_DEBUG] ? 1 : 0;
     P.dbuf = dbuf ? 1 : 0;
     {
         double ha[MPST_MAX_D], hb[MPST_MAX_D];

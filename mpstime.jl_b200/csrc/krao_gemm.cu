@@ -237,6 +237,9 @@ krao_reg_kernel(const double* __restrict__ x, const double* __restrict__ E, cons
 template <int NI>
 int launch_reg(mpst_ctx* c, const double* x, const double* E, const double* W, double* out, int64_t row_begin,
                int64_t row_end, int d, int chi, int n_out, int64_t ldw, int64_t ldo, size_t smem) {
+    c->last[L_KRAO_KERNEL] = 1;
+    c->last[L_KRAO_VARIANT] = NI;
+    c->last[L_KRAO_REG_MASK] |= 1 << NI;
     auto kern = krao_reg_kernel<NI>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t units = (row_end + 15) / 16 - row_begin / 16;
@@ -251,6 +254,8 @@ template <int TM, int TN, int WM, int WN>
 int launch_cfg(mpst_ctx* c, const double* x, const double* E, const double* W, double* out,
                int64_t row_begin, int64_t row_end, int d, int chi, int n_out, int64_t ldw, int64_t ldo) {
     const size_t smem = 16 + sizeof(double) * ((size_t)TM * chi + (size_t)TM * d + 2 * TM * LDP + 2 * TN * LDP);
+    c->last[L_KRAO_KERNEL] = 2;
+    c->last[L_KRAO_VARIANT] = TN;
     auto kern = krao_gemm_kernel<TM, TN, WM, WN>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -275,7 +280,7 @@ int launch_krao_gemm_rows(mpst_ctx* c, const double* x, const double* E, const d
 #define ARGS c, x, E, W, out, row_begin, row_end, d, chi, n_out, ldw, ldo
     // narrow outputs with W resident in shared memory: the register-operand kernel (needs 16-byte columns, d >= 4)
     if (n_out <= 48 && n_out >= 8 && d >= 4 && ((d * chi) % 4) == 0 && (ldw % 2) == 0 && row_end - row_begin >= 256 &&
-        !getenv("MPST_KRAO_NOREG")) {
+        !c->flag[F_KRAO_NOREG]) {
         const int NIc = (n_out + 7) / 8;
         const size_t smem = 16 + sizeof(double) * ((size_t)8 * NIc * kr_pitch4(d * chi) + (size_t)8 * 16 * (kr_pitch4(d) + kr_pitch4(chi)));
         if (smem <= 227 * 1024) {

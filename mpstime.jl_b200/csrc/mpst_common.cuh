@@ -39,6 +39,38 @@ struct Timer {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
 
+// Run-time switches for tests / experiments.  They are read from the environment (MPST_<NAME>) exactly ONCE, in
+// mpst_create, and can be changed afterwards only through mpst_debug_set: a stray variable on one rank cannot
+// change the numerics half-way through a sharded sweep, and nothing on the per-bond path calls getenv().
+enum {
+    F_DENSE_FWD = 0, F_NO_ENV_REUSE, F_GRAD_T128, F_GRAD_NOKR, F_IMPUTE_NODBUF, F_IMPUTE_DEBUG, F_KRAO_NOREG,
+    F_SVD_INNER, F_SVD_DEBUG, F_SVD_SKIP, F_SVD_FIXED, F_SVD_FULL, F_SVD_PB64, F_SVD_LEGACY, F_SVD_NOSUB, F_SVD_OVS,
+    F_SVD_NOHALF, F_SVD_HALF_FROM, F_SVD_IT, F_SVD_NOGRAPH, F_GRAD_KC, F_COUNT
+};
+// which code path the last call took (mpst_debug_get): lets the parity tests assert that they exercised the
+// kernels the benchmark runs, and lets bench.py name the kernel it reports a roofline for
+enum {
+    L_SVD_PATH = 0,    // 1 tall-Gram, 2 wide-Gram, 3 subspace iteration, 4 fused Jacobi, 5 three-kernel Jacobi
+    L_SVD_ITERS,       // subspace iterations of the last split
+    L_SVD_RESTARTS,    // restarts without the column-scaling shortcut
+    L_GRAD_KERNEL,     // 1 bond_grad_kr_kernel (register operands), 2 bond_grad_kernel (shared-memory tiles)
+    L_GRAD_VARIANT,    // kr: MA*1000 + S*100 + KC;  tiles: TP*1000 + TQ
+    L_KRAO_KERNEL,     // 1 krao_reg_kernel, 2 krao_gemm_kernel
+    L_KRAO_VARIANT,    // reg: NI;  tiles: TN
+    L_FWD_PATH,        // 1 factorised + cached environment, 2 factorised, 3 dense
+    L_KRAO_REG_MASK,   // bit NI set for every krao_reg_kernel<NI> launched since the mask was last cleared (debug_set)
+    L_COUNT
+};
+
+struct SegTable {       // cached stream-K schedule of one (kernel variant, shape, class ranges) combination
+    std::vector<int64_t> key;
+    GradSeg* segs = nullptr;     // device
+    int* cta_ptr = nullptr;
+    int* tile_slot = nullptr;
+    int nseg = 0;
+    uint64_t last_use = 0;
+};
+
 struct mpst_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -70,13 +102,13 @@ struct mpst_ctx {
     size_t redcap = 0;
     double* scal = nullptr;     // device scalars [16]
     double* hscal = nullptr;    // pinned host mirror
-    GradSeg* segs = nullptr;    // device segment table
-    int* cta_ptr = nullptr;
-    int* tile_slot = nullptr;
-    size_t segcap = 0;
-    GradSeg* hsegs = nullptr;   // pinned
-    int* hcta_ptr = nullptr;
-    int* htile_slot = nullptr;
+    std::vector<SegTable> segtabs;   // stream-K schedules, built once per shape (no per-bond host work / sync)
+    uint64_t seg_clock = 0;
+    int flag[F_COUNT] = {0};
+    int last[L_COUNT] = {0};
+    // cursor of mpst_sweep_bonds: next bond of the (backward, forward) cycle, -1 = not started
+    int sw_cursor = -1;
+    int* nonfinite = nullptr;   // device flag: a loss / gradient weight / norm was NaN or Inf (checked once per bond)
     // jacobi workspace
     double* S = nullptr;        // (m+n) x npad column-major
     size_t Scap = 0;
@@ -163,6 +195,11 @@ int launch_scale_dev(mpst_ctx* c, double* v, int64_t n, const double* norm2_dev)
 int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* missing, int64_t n,
                  int method, const double* xgrid, int G, const double* uniforms, int n_traj,
                  double max_jump, double* out);
+
+// stream-K schedule cache (api.cu)
+SegTable* segtable_find(mpst_ctx* c, const std::vector<int64_t>& key);
+int segtable_add(mpst_ctx* c, const std::vector<int64_t>& key, const std::vector<GradSeg>& segs,
+                 const std::vector<int>& cta_ptr, const std::vector<int>& tile_slot, SegTable** out);
 
 // profiling helpers
 void prof_begin(mpst_ctx* c, int kind);

@@ -536,7 +536,7 @@ static int jacobi_sweeps(mpst_ctx* c, int m, int n, int npad, int64_t ld, double
     // with every relative off-diagonal <= 1e-8 ends with them <= ~1e-16: stop after it, no verification sweep.
     const double conv = 1e-8;
     const double abs_tol = std::max(1e-30, std::min(0.5 * eps, 1e-6 * cutoff));
-    const int inner = getenv("MPST_SVD_INNER") ? atoi(getenv("MPST_SVD_INNER")) : 1;
+    const int inner = c->flag[F_SVD_INNER];
     const size_t solve_smem = 2 * sizeof(double) * PB * (PB + 1);
     CUDA_TRY(c, cudaFuncSetAttribute(jac_solve_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
     int sweeps = 0;
@@ -558,7 +558,7 @@ static int jacobi_sweeps(mpst_ctx* c, int m, int n, int npad, int64_t ld, double
         if (sweeps < 64) { char b[32]; snprintf(b, sizeof b, " %.2e", c->hscal[8]); hist += b; }
         if (!(c->hscal[8] == c->hscal[8])) break;                 // NaN in the bond tensor
     }
-    if (getenv("MPST_SVD_DEBUG")) fprintf(stderr, "[svd] m=%d n=%d PB=%d sweeps=%d:%s\n", m, n, PB, sweeps, hist.c_str());
+    if (c->flag[F_SVD_DEBUG]) fprintf(stderr, "[svd] m=%d n=%d PB=%d sweeps=%d:%s\n", m, n, PB, sweeps, hist.c_str());
     if (!converged) {
         char b[160];
         snprintf(b, sizeof b, "svd: Jacobi did not converge (m=%d n=%d conv=%.2e) max-offdiag per sweep:", m, n, conv);
@@ -596,10 +596,10 @@ static int jacobi_sweeps_fused(mpst_ctx* c, int m, int n, int npad, int64_t ld, 
     const double eps = 2.220446049250313e-16;
     a.abs_tol = std::max(1e-30, std::min(0.5 * eps, 1e-6 * cutoff));
     a.trace_dev = trace_dev;
-    a.inner = getenv("MPST_SVD_INNER") ? atoi(getenv("MPST_SVD_INNER")) : 1;
-    a.skip = getenv("MPST_SVD_SKIP") ? atoi(getenv("MPST_SVD_SKIP")) : 0;
-    const int fixed = getenv("MPST_SVD_FIXED") ? atoi(getenv("MPST_SVD_FIXED")) : 0;
-    const bool partial = !getenv("MPST_SVD_FULL");
+    a.inner = c->flag[F_SVD_INNER];
+    a.skip = c->flag[F_SVD_SKIP];
+    const int fixed = c->flag[F_SVD_FIXED];
+    const bool partial = !c->flag[F_SVD_FULL];
     a.theta = c->scal + 6;
     CUDA_TRY(c, cudaMemsetAsync(c->scal + 6, 0, sizeof(double), c->stream));
     const double conv = 1e-8;
@@ -627,7 +627,7 @@ static int jacobi_sweeps_fused(mpst_ctx* c, int m, int n, int npad, int64_t ld, 
         if (sweeps < 64) { char b[32]; snprintf(b, sizeof b, " %.2e", c->hscal[8]); hist += b; }
         if (!(c->hscal[8] == c->hscal[8])) break;
     }
-    if (getenv("MPST_SVD_DEBUG")) fprintf(stderr, "[svd fused] m=%d n=%d R=%d sweeps=%d t=%.3f ms:%s\n", m, n, R, sweeps,
+    if (c->flag[F_SVD_DEBUG]) fprintf(stderr, "[svd fused] m=%d n=%d R=%d sweeps=%d t=%.3f ms:%s\n", m, n, R, sweeps,
                                           1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), hist.c_str());
     if (!converged) {
         char b[160];
@@ -648,7 +648,7 @@ int svd_split_device(mpst_ctx* c, const double* B, int Dl, int Dr, int C, int go
                      int* chi_new, double* sigma_host, int* sweeps_out) {
     const int n = going_left ? Dr : Dl;
     const int m = C * (going_left ? Dl : Dr);
-    const bool wide = getenv("MPST_SVD_PB64") != nullptr && n >= 256;
+    const bool wide = c->flag[F_SVD_PB64] && n >= 256;
     const int PBsel = wide ? 64 : 32;
     const int npad = (int)round_up(n, PBsel);
     const int mm = m + n;
@@ -673,17 +673,19 @@ int svd_split_device(mpst_ctx* c, const double* B, int Dl, int Dr, int C, int go
         if (done) return MPST_OK;
     }
     bool fused = false;
-    if (!wide && !getenv("MPST_SVD_LEGACY")) TRY(jacobi_sweeps_fused(c, m, n, npad, ld, cutoff, chi_max, trace_dev, sweeps_out, &fused));
+    if (!wide && !c->flag[F_SVD_LEGACY]) TRY(jacobi_sweeps_fused(c, m, n, npad, ld, cutoff, chi_max, trace_dev, sweeps_out, &fused));
     if (!fused) {
         if (wide) TRY(jacobi_sweeps<64>(c, m, n, npad, ld, cutoff, trace_dev, sweeps_out));
         else TRY(jacobi_sweeps<32>(c, m, n, npad, ld, cutoff, trace_dev, sweeps_out));
     }
+    c->last[L_SVD_PATH] = fused ? 4 : 5;
+    c->last[L_SVD_ITERS] = 0;
     jac_colnorm_kernel<<<npad, 128, 0, c->stream>>>(c->S, ld, m, c->colnorm);
     jac_sort_trunc_kernel<<<1, 1024, 0, c->stream>>>(c->colnorm, n, npad, chi_max, cutoff, c->perm, c->colnorm + npad, c->iscal);
     jac_gather_kernel<<<2 * c->sm_count, 256, 0, c->stream>>>(c->S, ld, m, n, C, c->perm, c->iscal, label_core, ortho_core);
     c->launches += 3;
     CUDA_TRY(c, cudaGetLastError());
-    CUDA_TRY(c, cudaMemcpyAsync(c->hiscal, c->iscal, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->hiscal, c->iscal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));   // chi_new, non-finite flag
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     *chi_new = c->hiscal[0];
     if (sigma_host) {

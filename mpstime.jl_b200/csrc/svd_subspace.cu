@@ -524,7 +524,8 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
                         const double* trace_dev, double* label_core, double* ortho_core, int* chi_new,
                         double* sigma_host, bool* done) {
     *done = false;
-    if (getenv("MPST_SVD_NOSUB") || cutoff < 1e-12) return MPST_OK;
+    c->last[L_SVD_RESTARTS] = 0;
+    if (c->flag[F_SVD_NOSUB] || cutoff < 1e-12) return MPST_OK;
     const int k = std::min(chi_max, std::min(m, n));
     const int PMAX = 112, MAXSPLIT = 16;
     int mode;                                                          // 0 tall-Gram, 1 wide-Gram, 2 subspace
@@ -535,7 +536,7 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         mode = 2;
         // measured on trained bonds (k = 40): p = 80 with 5 iterations beats p = 96 with 4 and p = 112 with 3 --
         // the p^3 single-CTA kernels (Cholesky, Rayleigh-Ritz eigen-solver) dominate, not the GEMMs
-        p = std::min((int)round_up(2 * k + (getenv("MPST_SVD_OVS") ? atoi(getenv("MPST_SVD_OVS")) : 0), 16), PMAX);
+        p = std::min((int)round_up(2 * k + c->flag[F_SVD_OVS], 16), PMAX);
         if (p < k + 32 || n <= p || m < p) return MPST_OK;            // too little oversampling: full Jacobi
     }
     const size_t need = (size_t)2 * n * p + (size_t)2 * m * p + (size_t)(MAXSPLIT + 4) * p * p + (size_t)n * k +
@@ -557,12 +558,14 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     unsigned long long* resbits = reinterpret_cast<unsigned long long*>(c->scal + 10);
     const size_t eig_smem = 2 * sizeof(double) * (size_t)p * (p + 1) + sizeof(double) * p + sizeof(int) * p + 16;
     CUDA_TRY(c, cudaMemsetAsync(status, 0, sizeof(int), c->stream));
-    const bool dbg = getenv("MPST_SVD_DEBUG") != nullptr;
+    const bool dbg = c->flag[F_SVD_DEBUG] != 0;
     if (dbg) cudaStreamSynchronize(c->stream);
     const auto t0 = std::chrono::steady_clock::now();
 
     auto finish = [&](const char* what, int iters, double res) -> int {
         *chi_new = c->hiscal[0];
+        c->last[L_SVD_PATH] = mode == 0 ? 1 : (mode == 1 ? 2 : 3);
+        c->last[L_SVD_ITERS] = iters;
         scatter_label_kernel<<<2 * c->sm_count, 256, 0, c->stream>>>(Uk, m, m / C, c->iscal, label_core);
         c->launches++;
         CUDA_TRY(c, cudaGetLastError());
@@ -601,7 +604,7 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
                                           cudaMemcpyDeviceToDevice, c->stream));
             TRY(launch_dgemm(c, 1, 0, n, k, m, M, ldm, Uk, m, ortho_core, n));
         }
-        CUDA_TRY(c, cudaMemcpyAsync(c->hiscal, c->iscal, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->hiscal, c->iscal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));   // chi_new, non-finite flag
         CUDA_TRY(c, cudaMemcpyAsync(c->hiscal + 8, status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         if (c->hiscal[8] != 0) return MPST_OK;
@@ -637,16 +640,16 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     // instead of orthonormalised.  If that ever makes a Cholesky pivot break down on a bond, the bond is flagged and
     // this call restarts with full orthonormalisation, so the shortcut can cost time but never correctness.
     const int slot0 = (c->svd_slot >= 0 && c->svd_slot < (int)c->svd_its.size()) ? c->svd_slot : -1;
-    bool half_orth = slot0 >= 0 && !c->svd_nohalf[slot0] && !getenv("MPST_SVD_NOHALF");
-    const int half_from = getenv("MPST_SVD_HALF_FROM") ? atoi(getenv("MPST_SVD_HALF_FROM")) : 1;
+    bool half_orth = slot0 >= 0 && !c->svd_nohalf[slot0] && !c->flag[F_SVD_NOHALF];
+    const int half_from = c->flag[F_SVD_HALF_FROM];
 restart:
     for (int round = 0; round < max_rounds; round++) {
         // iterations of the first round: 5 unless this bond's previous visits showed that fewer reach the residual
         // bound (trained spectra change slowly from sweep to sweep); a visit that needs a second round raises the
         // bond's floor for good, so every level is tried at most once per bond
         const int slot = (c->svd_slot >= 0 && c->svd_slot < (int)c->svd_its.size()) ? c->svd_slot : -1;
-        int first = getenv("MPST_SVD_IT") ? atoi(getenv("MPST_SVD_IT")) : (p >= 2 * k ? 5 : 7);
-        if (slot >= 0 && c->svd_its[slot] > 0 && !getenv("MPST_SVD_IT")) first = c->svd_its[slot];
+        int first = c->flag[F_SVD_IT] > 0 ? c->flag[F_SVD_IT] : (p >= 2 * k ? 5 : 7);
+        if (slot >= 0 && c->svd_its[slot] > 0 && c->flag[F_SVD_IT] <= 0) first = c->svd_its[slot];
         const int niter = round == 0 ? first : 3;
         for (int it = 0; it < niter; it++) {
             TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, Qa, n, Za, m));            // Z = M Q
@@ -682,7 +685,7 @@ restart:
         residual_kernel<<<k, 256, 0, c->stream>>>(T2, ortho_core, ev + p, c->iscal, n, resbits);
         c->launches++;
         CUDA_TRY(c, cudaGetLastError());
-        CUDA_TRY(c, cudaMemcpyAsync(c->hiscal, c->iscal, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->hiscal, c->iscal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));   // chi_new, non-finite flag
         CUDA_TRY(c, cudaMemcpyAsync(c->hiscal + 8, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(c->hscal + 10, resbits, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -691,6 +694,7 @@ restart:
             if (half_orth) {                                                       // retry once without the shortcut
                 if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d breakdown with column scaling -> restart with full orth\n", m, n);
                 c->svd_nohalf[slot0] = 1;
+                c->last[L_SVD_RESTARTS]++;
                 half_orth = false;
                 iters_done = 0;
                 CUDA_TRY(c, cudaMemsetAsync(status, 0, sizeof(int), c->stream));

@@ -7,7 +7,8 @@ from .core import BASIS_IDS, BASIS_RANGE
 
 
 def encoding_range(basis):
-    return BASIS_RANGE[BASIS_IDS[basis.lower()]]
+    """Domain of a basis; accepts the reference's spellings ("Legendre_No_Norm", ":legendre", Symbol-style)."""
+    return BASIS_RANGE[BASIS_IDS[str(basis).lower().lstrip(":")]]
 
 
 class Norms:

@@ -252,7 +252,7 @@ def test_free_running_sweep_matches_oracle(ctx, oracle, pkg):
     assert np.array_equal(np.argmax(yd * yd, 1), np.argmax(yr * yr, 1))
 
 
-def test_cached_environment_reuse_is_bit_exact(ctx, oracle, pkg, monkeypatch):
+def test_cached_environment_reuse_is_bit_exact(ctx, oracle, pkg):
     """The sweep takes the unlabelled forward factor from the environment slot of that site when the slot's provenance
     (core version, neighbour slot version, direction) says it is still current.  Same kernel, same operands: the whole
     trajectory must be bit-identical to recomputing the factor at every bond (MPST_NO_ENV_REUSE)."""
@@ -260,11 +260,14 @@ def test_cached_environment_reuse_is_bit_exact(ctx, oracle, pkg, monkeypatch):
     Xs, phi, ys, counts, cores = _problem(oracle, N, T, d, C)
     out = []
     for no_reuse in (False, True):
-        if no_reuse:
-            monkeypatch.setenv("MPST_NO_ENV_REUSE", "1")
-        ctx.train_load_x(Xs, counts, d, 12)
-        ctx.set_cores(cores)
-        lo, gn, chi = ctx.sweep(pkg.make_opts(chi_max=12, eta=0.05), 2)
+        ctx.debug_set("NO_ENV_REUSE", int(no_reuse))
+        try:
+            ctx.train_load_x(Xs, counts, d, 12)
+            ctx.set_cores(cores)
+            lo, gn, chi = ctx.sweep(pkg.make_opts(chi_max=12, eta=0.05), 2)
+            assert ctx.debug_get("fwd_path") == (2 if no_reuse else 1)
+        finally:
+            ctx.debug_set("NO_ENV_REUSE", 0)
         out.append((lo, gn, chi, ctx.get_cores()))
     (l0, g0, c0, k0), (l1, g1, c1, k1) = out
     assert np.array_equal(l0, l1) and np.array_equal(g0, g1) and np.array_equal(c0, c1)
@@ -275,8 +278,10 @@ def test_cached_environment_reuse_is_bit_exact(ctx, oracle, pkg, monkeypatch):
     ctx.build_env(True)
     l_a, g_a, _ = ctx.bond_step(T - 2, True, pkg.make_opts(chi_max=12, eta=0.05))
     ctx.set_cores(cores)
-    ctx.set_core(T - 2, 0.5 * cores[T - 2])                      # same shape, different values, environments untouched
+    ctx.build_env(True)
+    ctx.set_core(T - 2, 0.5 * cores[T - 2])                      # same shape, different values; slot T-2 is now stale
     l_b, g_b, _ = ctx.bond_step(T - 2, True, pkg.make_opts(chi_max=12, eta=0.05))
+    assert ctx.debug_get("fwd_path") == 2                        # the stale slot was not used as the forward factor
     cs = [c.copy() for c in cores]
     cs[T - 2] = 0.5 * cores[T - 2]
     assert l_b != l_a

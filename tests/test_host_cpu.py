@@ -163,4 +163,5 @@ def test_bench_reference_arm_contract():
     assert line["unit"] == "sample-bonds/s" and line["higher_is_better"] is True and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
-    assert line["config"]["workload"].startswith("trendy_sine_N100k_T100_d12_chi40")
+    assert line["config"]["workload"].startswith("north_star_trendy_sine_N1M_T256_d16_chi64")
+    assert line["scaling"] == "strong"

@@ -153,3 +153,60 @@ def test_imputation_gram_equals_qr(oracle):
     u = [0.5, 0.5, 0.5]
     out2, idx2 = oracle.impute_series(cls, x, missing, grid, genc, d, method="ITS", uniforms=u)
     assert np.array_equal(idx, idx2)                        # ITS at u = 1/2 is the median
+
+
+def test_c_restatement_of_hot_loop_matches_numpy_oracle(oracle):
+    """oracle/bond_ref.c (the timed CPU baseline's hot loop) against the literal numpy loop and the vectorised form:
+    KLD loss + gradient (1 and 3 threads, both normalisations) and the environment update."""
+    import bond_ref
+    rng = np.random.default_rng(5)
+    N, d, cl, cr, C = 70, 3, 4, 5, 2
+    counts = np.array([30, 40])
+    xl = oracle.legendre_encode(rng.uniform(-1, 1, N), d)
+    xr = oracle.legendre_encode(rng.uniform(-1, 1, N), d)
+    L = rng.standard_normal((N, cl))
+    R = rng.standard_normal((N, cr))
+    B = rng.standard_normal((d * cl * d * cr, C))
+    for sep in (False, True):
+        lo_l, G_l = oracle.loss_grad_KLD_loop(B, L, R, xl, xr, counts, sep)
+        lo_v, G_v = oracle.loss_grad_KLD(B, L, R, xl, xr, counts, sep)
+        for nt in (1, 3):
+            lo_c, G_c = bond_ref.loss_grad_kld(B, L, R, xl, xr, counts, sep, nt)
+            assert abs(lo_c - lo_l) <= 1e-12 * abs(lo_l) and abs(lo_c - lo_v) <= 1e-12 * abs(lo_v)
+            assert np.abs(G_c - G_l).max() <= 1e-11 * np.abs(G_l).max()
+            assert np.abs(G_c - G_v).max() <= 1e-11 * np.abs(G_v).max()
+    core = rng.standard_normal((cl, d, 6))
+    env = bond_ref.env_update(xl, L, core.transpose(1, 0, 2).reshape(-1, order="F"), 6)      # [s + d*(a + chi*k)]
+    assert np.abs(env - oracle.env_step_left(xl, L, core)).max() < 1e-12
+
+
+def test_reference_trained_mps_pins_layout_norm_and_classification(oracle):
+    """The reference's OWN trained MPS (ECG200 fixture, extracted by tests/golden/make_golden_mps_from_jld2.py) pins the
+    oracle's core index order, label position, normalize! and contract_mps/classify: with the reference's own encoded
+    training set (ecg200_legendre.npz) the overlaps must classify all 100 training series correctly (the fixture is a
+    converged fit) and <W|W> must be 1 -- any wrong index order or conjugation breaks both."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ecg200_trained_mps.npz"))
+    e = np.load(os.path.join(os.path.dirname(__file__), "golden", "ecg200_legendre.npz"))
+    T = 96
+    cores = [g["core_%02d" % j] for j in range(T)]
+    assert int(g["label_pos"]) == T - 1
+    assert cores[0].shape[0] == 1 and cores[-1].shape[2] == 1 and cores[-1].shape[3] == 2
+    assert max(A.shape[2] for A in cores) == 25                       # the fixture's chi_max
+    assert abs(oracle._norm2_general(cores) - 1.0) < 1e-12             # normalize!(W), RealRealHighDimension.jl:852
+    y = np.r_[np.zeros(31, dtype=np.int64), np.ones(69, dtype=np.int64)]
+    yh = oracle.overlaps(cores, e["phi_ref"])
+    assert np.array_equal(np.argmax(yh * yh, axis=1), y)
+    assert np.array_equal(oracle.classify(cores, e["phi_ref"]), y)
+    # the last forward half-sweep leaves sites 0..T-2 left-orthonormal (U of decomposeBT, :177-196)
+    for A in cores[:-1]:
+        a, s, b = A.shape
+        M = A.reshape(a * s, b)
+        assert np.abs(M.T @ M - np.eye(b)).max() < 1e-10
+    # ... and the label core carries the singular values: its Gram matrix over (class, site) is diagonal
+    A = cores[-1][:, :, 0, :]
+    Gm = np.einsum("asc,bsc->ab", A, A)
+    assert np.abs(Gm - np.diag(np.diag(Gm))).max() < 1e-10 * np.abs(Gm).max()
+    sig = np.sqrt(np.sort(np.diag(Gm))[::-1])
+    assert np.all(np.diff(np.sqrt(np.diag(Gm))) <= 1e-12)              # sorted descending as LAPACK returns them
+    # truncate! with cutoff 1e-10 kept them all: the discarded tail is below the cutoff only if nothing smaller exists
+    assert sig[-1] ** 2 / np.sum(sig ** 2) > 1e-10
