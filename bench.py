@@ -390,6 +390,14 @@ def pinned_copy(a):
 _PINNED = []
 
 
+_T0 = time.time()
+
+
+def log(rank, msg):
+    if rank == 0:
+        print("[bench %.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
+
+
 def fits_on_gpu(local, w, n_local):
     """Environment ring + series + work buffers of the workload against free device memory."""
     try:
@@ -429,10 +437,14 @@ def run_training(m, ctx, w, args, rank, world, local, td, steps, warmup, fp64_pe
     ctx.train_load_x(Xs_sorted, counts, d, chi_max, n_global=N_global, counts_global=counts_global)
     ctx.set_cores(cores0)
     ctx.sweep_bonds(topts, nb_sweep, restart=True, record=False)           # one whole untimed sweep: links reach chi_max
+    cores_host = ctx.get_cores()                                            # trained, chi-saturated, label on the last site
+    log(rank, "warm sweep done")
     for _ in range(warmup):
         ctx.sweep_bonds(topts, bps, record=False)
     ctx.profile_enable(True)
     ctx.profile_reset()
+    ctx.debug_set("grad_kr_launches", 0)
+    ctx.debug_set("grad_tile_launches", 0)
     clocks = ClockSampler(local)
     barrier(td, local)
     if rank == 0:
@@ -451,12 +463,13 @@ def run_training(m, ctx, w, args, rank, world, local, td, steps, warmup, fp64_pe
     launches = ctx.launch_count() - l0
     prof = ctx.profile_get()
     ctx.profile_enable(False)
-    grad_kernel = GRAD_KERNEL_NAMES.get(ctx.debug_get("grad_kernel"), "?")
-    grad_variant = ctx.debug_get("grad_variant")
+    n_kr, n_tile = ctx.debug_get("grad_kr_launches"), ctx.debug_get("grad_tile_launches")
+    grad_kernel = GRAD_KERNEL_NAMES[1 if n_kr >= n_tile else 2]          # the kernel that ran most of the timed launches
+    grad_mix = {"bond_grad_kr_kernel": n_kr, "bond_grad_kernel": n_tile}
     ms = reduce_over_ranks(td, local, ms)
     sample_bonds = steps * bps * N_global
     value = sample_bonds / (ms * 1e-3)
-    cores_host = ctx.get_cores()
+    log(rank, "timed region done: %.1f ms per bond" % (ms / (steps * bps)))
 
     # ---- end-to-end arm: one fitMPS-style call from host buffers ---------------------------------------
     e2e = None
@@ -480,6 +493,7 @@ def run_training(m, ctx, w, args, rank, world, local, td, steps, warmup, fp64_pe
             ch = ctx.get_cores()
         barrier(td, local)
         e2e_s = reduce_over_ranks(td, local, time.time() - t0)
+        log(rank, "e2e done")
         e2e = {"value": n_e2e * nb_sweep * N_global / e2e_s, "unit": "sample-bonds/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "seconds": e2e_s, "calls_timed": n_e2e,
                "step": f"one whole sweep ({nb_sweep} bonds) per call: mpst_train_load_x (pinned host series) + mpst_set_core x T + "
@@ -491,7 +505,7 @@ def run_training(m, ctx, w, args, rank, world, local, td, steps, warmup, fp64_pe
     gk_ms, gk_n, gk_fl = prof["grad_kernel"]
     achieved = gk_fl / (gk_ms * 1e-3) / 1e12 if gk_ms > 0 else 0.0
     traffic, traffic_src = kernel_traffic(grad_kernel, d, chi_max)
-    roofline = {"bound": "tensor", "kernel": grad_kernel, "kernel_variant": grad_variant, "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": grad_kernel, "kernel_launch_mix": grad_mix, "achieved": achieved,
                 "peak": fp64_peak[0], "unit": "TFLOP/s", "frac": achieved / fp64_peak[0], "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": fp64_peak[1], "launches": gk_n,
                 "avg_launch_ms": gk_ms / max(gk_n, 1), "algorithmic_flops_per_launch": gk_fl / max(gk_n, 1),

@@ -147,6 +147,25 @@ int mpst_impute_batch(mpst_ctx* ctx, int class_idx, const double* X, const uint8
                       int64_t n, int method, const double* xgrid, int G, const double* uniforms,
                       int n_traj, double max_jump, double* out);
 
+/* ---- the keyword arguments of impute_median / impute_mean / impute_mode / impute_ITS (MPS_methods.jl:201-347) -- */
+typedef struct mpst_impute_opts {
+    int32_t backwards;           /* impute_order = :backwards (MPS_methods.jl:113-118); 0 = :forwards             */
+    int32_t get_err;             /* get_wmad (median, sampling_utils.jl:192-196) / get_std (mean, :89-97)         */
+    int32_t max_trials;          /* ITS: draws per site when rejecting (reference default 10)                     */
+    int32_t reserved;
+    double rejection_threshold;  /* ITS: accept when |x - median| < threshold * WMAD (:295-311); < 0 = :none      */
+    double max_jump;             /* mode: jump filter (:104-158); < 0 = nothing                                   */
+} mpst_impute_opts;
+/* As mpst_impute_batch with every option.  err_out (T x n_traj x n, or NULL): the method's error bar at each imputed
+ * site (WMAD for median with get_err and for ITS with rejection, standard deviation for mean with get_err, else 0).
+ * With rejection the uniforms are a flat stream per instance -- uniforms_per_instance >= n_traj * K_max * max_trials
+ * values, consumed in order over sites and trajectories exactly as the reference's shared MersenneTwister is
+ * (MPS_methods.jl:324); without rejection the layout is that of mpst_impute_batch and uniforms_per_instance is
+ * ignored. */
+int mpst_impute_batch_ex(mpst_ctx* ctx, int class_idx, const double* X, const uint8_t* missing, int64_t n, int method,
+                         const double* xgrid, int G, const double* uniforms, int64_t uniforms_per_instance,
+                         int n_traj, const mpst_impute_opts* opts, double* out, double* err_out);
+
 /* ---- test / benchmark entry: teacher-forced K2 in isolation on caller-provided operands
  *      (Loss_Grad_KLD / Loss_Grad_MSE, loss_functions.jl:322-432, 561-619).
  *      B: D x C; L: chi_l x N; R: chi_r x N; xl, xr: d x N (all column-major, i.e. one sample per

@@ -19,6 +19,12 @@ class TrainOpts(C.Structure):
                 ("chi_max", C.c_int32), ("reserved", C.c_int32), ("eta", C.c_double), ("cutoff", C.c_double)]
 
 
+class ImputeOpts(C.Structure):
+    """mpst_impute_opts"""
+    _fields_ = [("backwards", C.c_int32), ("get_err", C.c_int32), ("max_trials", C.c_int32), ("reserved", C.c_int32),
+                ("rejection_threshold", C.c_double), ("max_jump", C.c_double)]
+
+
 # name -> (restype, argtypes): every symbol include/mpstime_b200.h declares
 SIGNATURES = {
     "mpst_version": (C.c_int, []),
@@ -44,6 +50,9 @@ SIGNATURES = {
     "mpst_overlaps": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_i64_p]),
     "mpst_impute_batch": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_u8_p, C.c_int64, C.c_int, c_double_p,
                                     C.c_int, c_double_p, C.c_int, C.c_double, c_double_p]),
+    "mpst_impute_batch_ex": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_u8_p, C.c_int64, C.c_int, c_double_p,
+                                       C.c_int, c_double_p, C.c_int64, C.c_int, C.POINTER(ImputeOpts), c_double_p,
+                                       c_double_p]),
     "mpst_bond_loss_grad": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                       C.c_int64, C.c_int, C.c_int, C.c_int, c_i64_p, C.c_int, C.c_int, C.c_int,
                                       c_double_p, c_double_p, c_double_p]),

@@ -299,10 +299,16 @@ def init_imputation_problem(mps: TrainedMPS, X_test, y_test=None, dx=1e-4, guess
 
 def get_predictions_batch(imp: ImputationProblem, cls, instances, missing_sites_list, method="median",
                           invert_transform=True, rseed=1, num_trajectories=1, max_jump=None, uniforms=None,
-                          device=None):
+                          device=None, impute_order="forwards", get_wmad=False, get_std=False,
+                          rejection_threshold=None, max_trials=10, return_err=False):
     """Batched get_predictions (imputation.jl:264-410): instances are indices into the test series of
-    class `cls`; missing_sites_list[k] are the 0-based sites to impute in instance k.
-    Returns (ts (n, n_traj, T), target (n, T))."""
+    class `cls`; missing_sites_list[k] are the 0-based sites to impute in instance k.  Keyword arguments are those of
+    impute_median / impute_mean / impute_mode / impute_ITS (MPS_methods.jl:201-347); `rejection_threshold=None` is the
+    reference's `:none`.  Returns (ts (n, n_traj, T), target (n, T)), or (ts, pred_err, target) with return_err:
+    pred_err (n, n_traj, T) holds WMAD (median, get_wmad) / std (mean, get_std) at the imputed sites, transformed back
+    like the reference does (:337-384: add the series, invert, subtract; values the logit cannot invert become NaN)."""
+    if method not in ("median", "mean", "mode", "ITS"):
+        raise ValueError("Invalid method. Choose :mean, :mode, :median or :ITS")
     ctx = _context(device)
     _load_model(ctx, imp.mps)
     opts = imp.opts
@@ -321,28 +327,37 @@ def get_predictions_batch(imp: ImputationProblem, cls, instances, missing_sites_
         # the reference draws rand(MersenneTwister(rseed)) site by site (MPS_methods.jl:324); callers
         # needing Julia's stream pass `uniforms` drawn in Julia
         rs = np.random.RandomState(rseed)
-        uniforms = rs.random_sample((n, num_trajectories, Kmax))
-    out = ctx.impute_batch(imp.class_map[cls], Xs, mask.T, imp.xvals, method=method, uniforms=uniforms,
-                           n_traj=num_trajectories if method == "ITS" else 1,
-                           max_jump=-1.0 if max_jump is None else float(max_jump))
+        per_site = max_trials if rejection_threshold is not None else 1
+        uniforms = rs.random_sample((n, num_trajectories, Kmax * per_site))
+    get_err = (method == "median" and get_wmad) or (method == "mean" and get_std)
+    out, err = ctx.impute_batch(imp.class_map[cls], Xs, mask.T, imp.xvals, method=method, uniforms=uniforms,
+                                n_traj=num_trajectories if method == "ITS" else 1,
+                                max_jump=-1.0 if max_jump is None else float(max_jump), impute_order=impute_order,
+                                get_err=get_err, rejection_threshold=rejection_threshold if method == "ITS" else None,
+                                max_trials=max_trials, return_err=True)
     if invert_transform:                                                   # :337-394
         res = np.empty_like(out)
         for tr in range(out.shape[1]):
             res[:, tr, :] = invert_test_transform(out[:, tr, :].T, oob, imp.norms, opts).T
-        return res, raw
+            if method in ("median", "mean"):                               # :340-379
+                with np.errstate(invalid="ignore"):
+                    err[:, tr, :] = invert_test_transform((err[:, tr, :] + out[:, tr, :]).T, oob, imp.norms, opts).T - res[:, tr, :]
+        return (res, err, raw) if return_err else (res, raw)
     full, _ = transform_test_data(raw.T, imp.norms, opts)
-    return out, full.T
+    return (out, err, full.T) if return_err else (out, full.T)
 
 
 def MPS_impute(imp: ImputationProblem, cls, instance, missing_sites, method="median", **kw):
     """MPS_impute(imp, class, instance, missing_sites, method) (imputation.jl:467-563) without the
     plotting / kNN-baseline extras: returns (imputed_ts list, pred_err, target, stats)."""
-    ts, target = get_predictions_batch(imp, cls, [instance], [missing_sites], method=method, **kw)
+    ts, err, target = get_predictions_batch(imp, cls, [instance], [missing_sites], method=method, return_err=True, **kw)
     ts = [ts[0, t] for t in range(ts.shape[1])]
     ms = list(missing_sites)
     stats = [{"MAE": float(np.mean(np.abs(t[ms] - target[0][ms]))),
               "MAPE": float(np.mean(np.abs((t[ms] - target[0][ms]) / target[0][ms])))} for t in ts]
-    return ts, [None for _ in ts], target[0], stats
+    # imputation.jl:299-318: only :mean and :median produce error bars; the others return `nothing` per trajectory
+    pred_err = [err[0, t] for t in range(len(ts))] if method in ("median", "mean") else [None for _ in ts]
+    return ts, pred_err, target[0], stats
 
 
 class MPSClassifier:

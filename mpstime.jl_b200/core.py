@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import TrainOpts, c_double_p, c_i32_p, c_i64_p, c_u8_p
+from ._lib import ImputeOpts, TrainOpts, c_double_p, c_i32_p, c_i64_p, c_u8_p
 
 BASIS_IDS = {
     "legendre_no_norm": 0, "legendre": 0, "legendre_norm": 1, "fourier": 2, "stoudenmire": 3,
@@ -205,7 +205,15 @@ class Context:
 
     # ---- K8 ---------------------------------------------------------------------------------
     def impute_batch(self, class_idx, X_TxN, missing_TxN, grid, method="median", uniforms=None, n_traj=1,
-                     max_jump=-1.0):
+                     max_jump=-1.0, impute_order="forwards", get_err=False, rejection_threshold=None, max_trials=10,
+                     return_err=False):
+        """K8.  Returns out (n, n_traj, T) [and err (n, n_traj, T) with return_err].  `uniforms`: (n, n_traj, K_max)
+        for plain ITS; with `rejection_threshold` a flat stream (n, U), U >= n_traj * K_max * max_trials."""
+        if impute_order not in ("forwards", "backwards"):
+            raise ValueError('impute_order must be either "forwards" or "backwards"')      # MPS_methods.jl:119
+        if get_err or return_err or rejection_threshold is not None or impute_order != "forwards":
+            return self._impute_batch_ex(class_idx, X_TxN, missing_TxN, grid, method, uniforms, n_traj, max_jump,
+                                         impute_order, get_err, rejection_threshold, max_trials, return_err)
         X = np.asarray(X_TxN, dtype=np.float64)
         T, n = X.shape
         Xh = np.ascontiguousarray(X.T)
@@ -219,6 +227,32 @@ class Context:
                                              METHOD_IDS[method], _dp(grid), len(grid),
                                              _dp(u) if u is not None else None, int(n_traj), float(max_jump), _dp(out)))
         return out
+
+    def _impute_batch_ex(self, class_idx, X_TxN, missing_TxN, grid, method, uniforms, n_traj, max_jump, impute_order,
+                         get_err, rejection_threshold, max_trials, return_err):
+        X = np.asarray(X_TxN, dtype=np.float64)
+        T, n = X.shape
+        Xh = np.ascontiguousarray(X.T)
+        mh = np.ascontiguousarray(np.asarray(missing_TxN, dtype=np.uint8).T)
+        grid = _f64(grid)
+        nt = n_traj if method == "ITS" else 1
+        out = np.empty((n, nt, T), dtype=np.float64)
+        err = np.zeros((n, nt, T), dtype=np.float64)
+        io = ImputeOpts()
+        io.backwards = int(impute_order == "backwards")
+        io.get_err = int(bool(get_err))
+        io.max_trials = int(max_trials)
+        io.rejection_threshold = -1.0 if rejection_threshold is None else float(rejection_threshold)
+        io.max_jump = -1.0 if max_jump is None else float(max_jump)
+        u, per = None, 0
+        if uniforms is not None:
+            u = _f64(uniforms)
+            per = u.size // max(n, 1)
+        self._chk(self.lib.mpst_impute_batch_ex(self.h, int(class_idx), _dp(Xh), mh.ctypes.data_as(c_u8_p), n,
+                                                METHOD_IDS[method], _dp(grid), len(grid),
+                                                _dp(u) if u is not None else None, int(per), int(nt), C.byref(io),
+                                                _dp(out), _dp(err)))
+        return (out, err) if return_err else out
 
     # ---- test entries -------------------------------------------------------------------------
     def bond_loss_grad(self, B, L, R, xl, xr, class_counts, loss="KLD", train_sep=False, want_yhat=False):

@@ -115,6 +115,16 @@ static bool env_fresh(const mpst_ctx* c, int j, int dir) {
            c->env_src_ver[j] == ((src >= 0 && src < c->T) ? c->env_ver[src] : 0);
 }
 
+// core `site` changed: every left environment at or right of it and every right environment at or left of it was
+// contracted through the old core.  env_fresh() only sees one level (own core, neighbour slot), so the dependents are
+// dropped here; `keep` is the slot that was just recomputed from the new core (-1: none).
+static void invalidate_dependents(mpst_ctx* c, int site, int keep) {
+    for (int j = 0; j < c->T; j++) {
+        if (j == keep || c->env_chi[j] == 0) continue;
+        if ((c->env_dir[j] == 1 && j >= site) || (c->env_dir[j] == 2 && j <= site)) c->env_chi[j] = 0;
+    }
+}
+
 static int core_orient(mpst_ctx* c, int site, int want) {
     Core& k = c->cores[site];
     if (k.orient == want) return MPST_OK;
@@ -204,7 +214,8 @@ const FlagDef kFlags[F_COUNT] = {
     {"GRAD_KC", 0, false},
 };
 const char* kLast[L_COUNT] = {"svd_path", "svd_iters", "svd_restarts", "grad_kernel", "grad_variant", "krao_kernel",
-                              "krao_variant", "fwd_path", "krao_reg_mask"};
+                              "krao_variant", "fwd_path", "krao_reg_mask", "grad_kr_launches", "grad_tile_launches", "svd_calls",
+                              "svd_iters_sum", "svd_round2", "svd_jacobi", "svd_fast"};
 void flags_from_env(mpst_ctx* c) {
     for (int f = 0; f < F_COUNT; f++) {
         c->flag[f] = kFlags[f].def;
@@ -383,6 +394,7 @@ static int model_reset(mpst_ctx* c, int T, int C, int d, int chi_max) {
     c->env_dir.assign(T, 0);
     c->sw_cursor = -1;
     c->svd_its.clear();
+    c->svd_hint_m = c->svd_hint_n = c->svd_hint_its = c->svd_hint_floor = 0;
     c->svd_floor.clear();
     c->svd_nohalf.clear();
     if ((int)c->cores.size() != T) {
@@ -492,6 +504,7 @@ int mpst_set_core(mpst_ctx* c, int site, const double* data, int chi_l, int chi_
     TRY(core_reserve(c, k, std::max(cap, n)));
     k.chi_l = chi_l; k.chi_r = chi_r; k.has_label = has_label ? 1 : 0; k.orient = ORIENT_LEFT;
     mark_core(c, site);
+    invalidate_dependents(c, site, -1);
     c->sw_cursor = -1;
     TRY(ensure_buf(c, &c->tmp, &c->tmpcap, n));
     CUDA_TRY(c, cudaMemcpyAsync(c->tmp, data, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -795,6 +808,8 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         c->prof_work[MPST_T_ENV] += 2.0 * (double)c->N * Dr * chi_new;
         c->env_chi[r] = chi_new;
         mark_env(c, r, 2);
+        invalidate_dependents(c, l, r);
+        invalidate_dependents(c, r, r);
     } else {                // W[l] <- U (LEFT), W[r] <- V*S with the label (RIGHT)   (:177-196)
         kl.chi_r = chi_new; kl.has_label = 0; kl.orient = ORIENT_LEFT;
         kr.chi_l = chi_new; kr.has_label = 1; kr.orient = ORIENT_RIGHT;
@@ -803,6 +818,8 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         c->prof_work[MPST_T_ENV] += 2.0 * (double)c->N * Dl * chi_new;
         c->env_chi[l] = chi_new;
         mark_env(c, l, 1);
+        invalidate_dependents(c, l, l);
+        invalidate_dependents(c, r, l);
     }
     if (chi_new_out) *chi_new_out = chi_new;
     return MPST_OK;
@@ -1090,7 +1107,19 @@ int mpst_bond_split(mpst_ctx* c, const double* B, int d, int chi_l, int chi_r, i
 int mpst_impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* missing, int64_t n, int method,
                       const double* xgrid, int G, const double* uniforms, int n_traj, double max_jump, double* out) {
     if (!c) return MPST_E_INVALID;
-    return impute_batch(c, class_idx, X, missing, n, method, xgrid, G, uniforms, n_traj, max_jump, out);
+    mpst_impute_opts io;
+    memset(&io, 0, sizeof io);
+    io.max_jump = max_jump;
+    io.rejection_threshold = -1.0;
+    io.max_trials = 10;
+    return impute_batch(c, class_idx, X, missing, n, method, xgrid, G, uniforms, 0, n_traj, &io, out, nullptr);
+}
+
+int mpst_impute_batch_ex(mpst_ctx* c, int class_idx, const double* X, const uint8_t* missing, int64_t n, int method,
+                         const double* xgrid, int G, const double* uniforms, int64_t uniforms_per_instance, int n_traj,
+                         const mpst_impute_opts* opts, double* out, double* err_out) {
+    if (!c || !opts) return MPST_E_INVALID;
+    return impute_batch(c, class_idx, X, missing, n, method, xgrid, G, uniforms, uniforms_per_instance, n_traj, opts, out, err_out);
 }
 
 int mpst_profile_enable(mpst_ctx* c, int on) { if (!c) return MPST_E_INVALID; c->prof = on != 0; return MPST_OK; }

@@ -299,6 +299,7 @@ int launch_bond_grad(mpst_ctx* c, const double* xl, const double* xr, const doub
     else kern = TP == 128 ? bond_grad_kernel<16, 4, 8> : bond_grad_kernel<16, 5, 6>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     c->last[L_GRAD_KERNEL] = 2;
+    c->last[L_GRAD_TILE_LAUNCHES]++;
     c->last[L_GRAD_VARIANT] = TP * 1000 + TQ;
     prof_begin(c, MPST_T_GRADK);
     kern<<<ncta, 256, smem, c->stream>>>(xl, xr, L, R, c->w, c->Npad, d, chi_l, chi_r, tab->segs, tab->cta_ptr, c->part);

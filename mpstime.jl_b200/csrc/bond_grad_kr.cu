@@ -18,8 +18,8 @@
 #include "dmma.cuh"
 
 namespace {
-constexpr int KC = 64;       // samples per pipeline stage
-constexpr int SR = 3;        // raw stages
+// KC = samples per pipeline stage, SR = raw stages: 64 x 3 where the ring fits in shared memory (config B:
+// 29.4 vs 27.5 TFLOP/s with 16-sample stages), 32 x 4 for wide links (d = 16, chi = 64: 160 doubles per sample).
 
 struct KrGeom {
     int nab, nsg, nbb, ntg;  // link blocks / site groups per side
@@ -27,7 +27,7 @@ struct KrGeom {
     int ngroups;             // ceil(units / warps per CTA)
 };
 
-template <int MA, int S, int NB, int T, int NW>
+template <int MA, int S, int NB, int T, int NW, int KC, int SR>
 __global__ void __launch_bounds__(32 * NW, 1)
 bond_grad_kr_kernel(const double* __restrict__ xl, const double* __restrict__ xr,
                     const double* __restrict__ L, const double* __restrict__ R,
@@ -209,7 +209,7 @@ grad_kr_reduce_kernel(const double* __restrict__ part, const int* __restrict__ g
     }
 }
 
-template <int MA, int S, int NB, int T, int NW>
+template <int MA, int S, int NB, int T, int NW, int KC, int SR>
 int launch_kr(mpst_ctx* c, const double* xl, const double* xr, const double* L, const double* R, int d, int chi_l,
               int chi_r, const int64_t* cls_begin, const int64_t* cls_end, int ncls, double* G, size_t smem) {
     KrGeom geo;
@@ -269,8 +269,9 @@ int launch_kr(mpst_ctx* c, const double* xl, const double* xr, const double* L, 
     constexpr int RU = MA * S * 8, CU = NB * T * 8;
     TRY(ensure_buf(c, &c->part, &c->partcap, (size_t)nseg * NW * RU * CU));
     c->last[L_GRAD_KERNEL] = 1;
+    c->last[L_GRAD_KR_LAUNCHES]++;
     c->last[L_GRAD_VARIANT] = MA * 1000 + S * 100 + KC;
-    auto kern = bond_grad_kr_kernel<MA, S, NB, T, NW>;
+    auto kern = bond_grad_kr_kernel<MA, S, NB, T, NW, KC, SR>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(c, MPST_T_GRADK);
     kern<<<ncta, 32 * NW, smem, c->stream>>>(xl, xr, L, R, c->w, c->Npad, d, chi_l, chi_r, geo, tab->segs, tab->cta_ptr, c->part);
@@ -292,15 +293,20 @@ int launch_bond_grad_kr(mpst_ctx* c, const double* xl, const double* xr, const d
     *handled = false;
     if (c->flag[F_GRAD_NOKR]) return MPST_OK;
     if ((chi_l & 1) || (chi_r & 1) || chi_l < 8 || chi_r < 8) return MPST_OK;       // 16-byte rows for the bulk copies
-    const size_t smem = 128 + sizeof(double) * (size_t)SR * (KC * (chi_l + chi_r + 2 * d) + KC);
-    if (smem > 227 * 1024) return MPST_OK;
+    auto ring = [&](int kc, int sr) { return 128 + sizeof(double) * (size_t)sr * (kc * (chi_l + chi_r + 2 * d) + kc); };
+    const int forced = c->flag[F_GRAD_KC];
+    const bool big = ring(64, 3) <= 227 * 1024 && forced != 32;
+    if (!big && ring(32, 4) > 227 * 1024) return MPST_OK;
+    const size_t smem = big ? ring(64, 3) : ring(32, 4);
     if (d % 6 == 0) {
         *handled = true;
-        return launch_kr<1, 6, 1, 6, 8>(c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem);
+        if (big) return launch_kr<1, 6, 1, 6, 8, 64, 3>(c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem);
+        return launch_kr<1, 6, 1, 6, 8, 32, 4>(c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem);
     }
     if (d % 4 == 0) {
         *handled = true;
-        return launch_kr<2, 4, 1, 4, 8>(c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem);
+        if (big) return launch_kr<2, 4, 1, 4, 8, 64, 3>(c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem);
+        return launch_kr<2, 4, 1, 4, 8, 32, 4>(c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem);
     }
     return MPST_OK;
 }

@@ -45,6 +45,11 @@ struct ImpParams {
     int dbuf;                       // 1: a second slice buffer fits in shared memory (asynchronous double-buffered staging)
     int64_t n;
     double max_jump;
+    double* err;                    // [n][ntraj][T] error bars (WMAD / std) or null
+    int get_err;                    // median: get_wmad, mean: get_std
+    int max_trials;                 // ITS with rejection: draws per site
+    double rej_thr;                 // ITS: accept when |x - median| < rej_thr * WMAD; < 0 = :none
+    int64_t ustride;                // rejection mode: uniforms per instance (flat stream, consumed in order)
 };
 
 __device__ __forceinline__ void encode_any(int basis, double x, int d, double* v) {
@@ -425,13 +430,16 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
         TOCK(1);
 
         // ---------------- forward pass(es) ---------------------------------------------------------
+        int64_t ucur = 0;                                     // position in this instance's uniform stream (rejection mode)
         for (int tr = 0; tr < P.ntraj; tr++) {
             double* xo = P.out + (inst * P.ntraj + tr) * T;
             for (int a = tid; a < n8; a += NT) vec[a] = (a == 0) ? 1.0 : 0.0;
             __syncthreads();
             int k = 0;
-            double x_prev = 0.0;
-            bool have_prev = false;
+            // x_prev of impute_at! (MPS_methods.jl:136-144, 158): the value next to the first site to impute if there
+            // is one, afterwards always the value imputed last -- known sites in between do NOT update it
+            double x_prev = first > 0 ? x[first - 1] : 0.0;
+            bool have_prev = first > 0;
             for (int j = 0; j <= last; j++) {
                 const int cl = P.chi[j], cr = P.chi[j + 1];
                 const double* A = P.cores + P.core_off[j];
@@ -444,8 +452,6 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                     double acc[2] = {0.0, 0.0};
                     for (int s = grp; s < d; s += 4) colsum_global(A + (size_t)s * cl * cr, cl, cr, phi[s], acc);
                     reduce_partials(acc, cr, vec2);
-                    x_prev = x[j];
-                    have_prev = true;
                     TOCK(2);
                 } else {
                     // A_d[s][b] = sum_a v[a] A[s][a][b]
@@ -523,6 +529,7 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                     TICK();
                     int gsel = 0;
                     double xsel = 0.0;
+                    double errv = 0.0;
                     if (P.method == MPST_IMPUTE_MEDIAN || P.method == MPST_IMPUTE_ITS) {
                         // cumulative trapezoid c[g] = c[g-1] + (p[g-1] + p[g]), scaled by h = (x1-x0)/2
                         double loc = 0.0;
@@ -538,23 +545,92 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                         const double pre_t = block_excl_scan(loc, scr, tot);
                         const double h = (P.grid[1] - P.grid[0]) * 0.5;
                         const double Z = h * tot;
-                        const double u = (P.method == MPST_IMPUTE_MEDIAN) ? 0.5
-                                         : P.uniforms[((size_t)inst * P.ntraj + tr) * P.Kmax + k];
-                        double best = 1e300;
-                        int bg = 0x7fffffff;
-                        double run = pre_t;
-                        const double uZ = u * Z;
-                        double prev = (g0 > 0 && g0 < g1) ? pbuf[g0 - 1] : 0.0;
-                        for (int g = g0; g < g1; g++) {
-                            const double cur = pbuf[g];
-                            if (g > 0) run += prev + cur;
-                            prev = cur;
-                            const double cg = h * run;
-                            const double val = fabs(cg - uZ);            // argmin |cdf/Z - u| without a division per point
-                            if (val < best) { best = val; bg = g; }
+                        // grid point whose cdf is closest to u: argmin |cdf/Z - u| without a division per point
+                        auto pick = [&](double u) -> int {
+                            double best = 1e300;
+                            int bg = 0x7fffffff;
+                            double run = pre_t;
+                            const double uZ = u * Z;
+                            double prev = (g0 > 0 && g0 < g1) ? pbuf[g0 - 1] : 0.0;
+                            for (int g = g0; g < g1; g++) {
+                                const double cur = pbuf[g];
+                                if (g > 0) run += prev + cur;
+                                prev = cur;
+                                const double val = fabs(h * run - uZ);
+                                if (val < best) { best = val; bg = g; }
+                            }
+                            int gs = block_argbest<false>(best, bg, scr);
+                            if (gs < 0 || gs >= G) gs = 0;            // non-finite pdf (NaN in the cores): stay in bounds
+                            return gs;
+                        };
+                        // weighted median absolute deviation about grid point m (sampling_utils.jl:192-196 ->
+                        // StatsBase median(v, pweights(w)) = quantile(v, w, 0.5)): the (|x_g - x_m|, p_g/Z) pairs sorted by
+                        // value then weight are m itself followed by the two points at grid distance 1, 2, ...; cumulative
+                        // weight S_k, h = (sum w - w_1)/2 + w_1, linear interpolation at the first S_k > h
+                        auto wmad = [&](int m) -> double {
+                            const double xm = P.grid[m];
+                            const double iZ = 1.0 / Z;
+                            const int J = max(m, G - 1 - m) + 1;      // distances 0 .. J-1
+                            const int perj = (J + NT - 1) / NT;
+                            const int j0 = min(J, tid * perj), j1 = min(J, j0 + perj);
+                            auto pairw = [&](int j, double* v, double* w) -> int {   // elements at distance j in sorted order
+                                if (j == 0) { v[0] = 0.0; w[0] = pbuf[m] * iZ; return 1; }
+                                int cnt = 0;
+                                if (m - j >= 0) { v[cnt] = fabs(P.grid[m - j] - xm); w[cnt] = pbuf[m - j] * iZ; cnt++; }
+                                if (m + j < G) { v[cnt] = fabs(P.grid[m + j] - xm); w[cnt] = pbuf[m + j] * iZ; cnt++; }
+                                if (cnt == 2 && (v[1] < v[0] || (v[1] == v[0] && w[1] < w[0]))) {
+                                    const double tv = v[0], tw = w[0]; v[0] = v[1]; w[0] = w[1]; v[1] = tv; w[1] = tw;
+                                }
+                                return cnt;
+                            };
+                            double lsum = 0.0;
+                            for (int j = j0; j < j1; j++) { double v[2], w[2]; const int cnt = pairw(j, v, w); for (int q = 0; q < cnt; q++) lsum += w[q]; }
+                            double wsum;
+                            double S = block_excl_scan(lsum, scr, wsum);
+                            const double w1 = pbuf[m] * iZ;
+                            const double hq = 0.5 * (wsum - w1) + w1;
+                            double vprev = 0.0;
+                            if (j0 > 0 && j0 < J) { double v[2], w[2]; const int cnt = pairw(j0 - 1, v, w); vprev = v[cnt - 1]; }
+                            int found = 0x7fffffff;
+                            double res = 0.0;
+                            for (int j = j0; j < j1 && found == 0x7fffffff; j++) {
+                                double v[2], w[2];
+                                const int cnt = pairw(j, v, w);
+                                for (int q = 0; q < cnt; q++) {
+                                    if (w[q] == 0.0) continue;                       // zero weights are dropped before sorting
+                                    const double Sold = S;
+                                    S += w[q];
+                                    if (S > hq) { found = 2 * j + q; res = vprev + (hq - Sold) / (S - Sold) * (v[q] - vprev); break; }
+                                    vprev = v[q];
+                                }
+                            }
+                            const int win = block_argbest<false>((double)found, tid, scr);      // thread holding the first crossing
+                            __syncthreads();
+                            if (tid == win) scr[0] = (found == 0x7fffffff) ? fmax(fabs(P.grid[0] - xm), fabs(P.grid[G - 1] - xm)) : res;
+                            __syncthreads();
+                            const double out = scr[0];
+                            __syncthreads();
+                            return out;
+                        };
+                        if (P.method == MPST_IMPUTE_MEDIAN) {
+                            gsel = pick(0.5);
+                            if (P.get_err) errv = wmad(gsel);
+                        } else if (P.rej_thr < 0.0) {
+                            gsel = pick(P.uniforms[((size_t)inst * P.ntraj + tr) * P.Kmax + k]);
+                        } else {
+                            // rejection sampling about the median (sampling_utils.jl:291-311): the flat uniform stream of
+                            // this instance is consumed in order, over sites and trajectories
+                            const int gm = pick(0.5);
+                            const double wm = wmad(gm);
+                            gsel = gm;
+                            for (int trial = 0; trial < P.max_trials; trial++) {
+                                const double u = P.uniforms[(size_t)inst * P.ustride + ucur];
+                                ucur++;
+                                gsel = pick(u);
+                                if (fabs(P.grid[gsel] - P.grid[gm]) < P.rej_thr * wm) break;
+                            }
+                            errv = wm;
                         }
-                        gsel = block_argbest<false>(best, bg, scr);
-                        if (gsel < 0 || gsel >= G) gsel = 0;          // non-finite pdf (NaN in the cores): stay in bounds
                         xsel = P.grid[gsel];
                     } else if (P.method == MPST_IMPUTE_MODE) {
                         double best = -1.0; int bg = 0x7fffffff;
@@ -582,9 +658,18 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                         const double Z = (P.grid[1] - P.grid[0]) * sp;
                         xsel = sxp * dx / Z;
                         gsel = -1;
+                        if (P.get_err) {                                  // sampling_utils.jl:89-97: sqrt(sum (x - E)^2 p dx / Z)
+                            double sv = 0.0;
+                            for (int g = g0; g < g1; g++) { const double df = P.grid[g] - xsel; sv += df * df * pbuf[g]; }
+                            sv = block_reduce_sum(sv, red);
+                            errv = sqrt(sv * dx / Z);
+                        }
                     }
                     TOCK(6);
-                    if (tid == 0) xo[j] = xsel;
+                    if (tid == 0) {
+                        xo[j] = xsel;
+                        if (P.err) P.err[(inst * P.ntraj + tr) * T + j] = errv;
+                    }
                     // state of the chosen value, then v <- state . A_d
                     if (gsel >= 0) { for (int s = tid; s < d; s += NT) phi[s] = P.genc[(size_t)gsel * d + s]; }
                     else if (tid == 0) encode_any(P.basis, xsel, d, phi);
@@ -629,7 +714,12 @@ __global__ void slice_core_kernel(CoreView v, int d, int chi_l, int chi_r, int c
 }  // namespace
 
 int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* missing, int64_t n, int method,
-                 const double* xgrid, int G, const double* uniforms, int n_traj, double max_jump, double* out) {
+                 const double* xgrid, int G, const double* uniforms, int64_t uniforms_per_instance, int n_traj,
+                 const mpst_impute_opts* io, double* out, double* err_out) {
+    const double max_jump = io ? io->max_jump : -1.0;
+    const bool backwards = io && io->backwards;
+    const bool rejection = io && method == MPST_IMPUTE_ITS && io->rejection_threshold >= 0.0;
+    if (rejection && io->max_trials < 1) { c->err = "impute_batch: max_trials must be positive"; return MPST_E_INVALID; }
     if (!X || !missing || !xgrid || !out || n < 0 || G < 2 || c->T == 0) { c->err = "impute_batch: bad arguments"; return MPST_E_INVALID; }
     if (class_idx < 0 || class_idx >= c->C) { c->err = "impute_batch: class index out of range"; return MPST_E_INVALID; }
     if (method < MPST_IMPUTE_MEDIAN || method > MPST_IMPUTE_ITS) { c->err = "impute_batch: unknown method"; return MPST_E_INVALID; }
@@ -643,17 +733,32 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     if (n_traj < 1) n_traj = 1;
     CUDA_TRY(c, cudaSetDevice(c->device));
     const int T = c->T, d = c->d;
+    // impute_order = :backwards (MPS_methods.jl:113-118: orthogonalize to the last site, walk right to left) is the
+    // forward walk on the mirrored chain: position p holds site T-1-p with its two links exchanged; series, masks and
+    // results are mirrored on the host.  pos(j) = chain position of site j.
+    auto pos = [&](int j) { return backwards ? T - 1 - j : j; };
     std::vector<int> chi(T + 1, 1);
     std::vector<int64_t> off(T, 0);
     int chimax = 1;
     int64_t tot = 0;
-    for (int j = 0; j < T; j++) {
-        const Core& k = c->cores[j];
+    for (int p = 0; p < T; p++) {
+        const Core& k = c->cores[pos(p)];
         if (!k.dev) { c->err = "impute_batch: cores not set"; return MPST_E_INVALID; }
-        chi[j] = k.chi_l; chi[j + 1] = k.chi_r;
+        chi[p] = backwards ? k.chi_r : k.chi_l;
+        chi[p + 1] = backwards ? k.chi_l : k.chi_r;
         chimax = std::max(chimax, std::max(k.chi_l, k.chi_r));
-        off[j] = tot;
+        off[p] = tot;
         tot += (int64_t)d * k.chi_l * k.chi_r;
+    }
+    std::vector<double> Xrev;
+    std::vector<uint8_t> Mrev;
+    if (backwards) {
+        Xrev.resize((size_t)n * T);
+        Mrev.resize((size_t)n * T);
+        for (int64_t i = 0; i < n; i++)
+            for (int j = 0; j < T; j++) { Xrev[i * T + j] = X[i * T + T - 1 - j]; Mrev[i * T + j] = missing[i * T + T - 1 - j]; }
+        X = Xrev.data();
+        missing = Mrev.data();
     }
     const auto t_begin = std::chrono::steady_clock::now();
     const int n8 = (chimax + 7) & ~7, ld = n8 + 4;
@@ -665,9 +770,21 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     // host-side Kmax
     int Kmax = 0;
     for (int64_t i = 0; i < n; i++) { int k = 0; for (int j = 0; j < T; j++) k += missing[i * T + j] ? 1 : 0; Kmax = std::max(Kmax, k); }
-    if (Kmax == 0) { for (int64_t i = 0; i < n; i++) for (int tr = 0; tr < n_traj; tr++) memcpy(out + (i * n_traj + tr) * T, X + i * T, sizeof(double) * T); return MPST_OK; }
+    if (err_out) memset(err_out, 0, sizeof(double) * (size_t)n * n_traj * T);
+    if (Kmax == 0) {
+        for (int64_t i = 0; i < n; i++)
+            for (int tr = 0; tr < n_traj; tr++)
+                for (int j = 0; j < T; j++) out[(i * n_traj + tr) * T + j] = X[i * T + pos(j)];
+        return MPST_OK;
+    }
+    const int64_t ustride = rejection ? uniforms_per_instance : (int64_t)n_traj * Kmax;
+    if (rejection && ustride < (int64_t)n_traj * Kmax * io->max_trials) {
+        c->err = "impute_batch: rejection sampling needs n_traj * K_max * max_trials uniforms per instance";
+        return MPST_E_INVALID;
+    }
     const int grid = (int)std::min<int64_t>(n, (int64_t)c->sm_count);       // one resident CTA per SM (shared memory), instances strided
     double *dcores = nullptr, *dX = nullptr, *dgrid = nullptr, *dgenc = nullptr, *dunif = nullptr, *dout = nullptr, *dGR = nullptr, *dp = nullptr;
+    double* derr = nullptr;
     uint8_t* dmask = nullptr;
     int64_t* doff = nullptr;
     int* dchi = nullptr;
@@ -693,22 +810,27 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     IMP_TRY(reserve(8, sizeof(int64_t) * T, (void**)&doff));
     IMP_TRY(reserve(9, sizeof(int) * (T + 1), (void**)&dchi));
     if (uniforms) {
-        IMP_TRY(reserve(10, sizeof(double) * n * n_traj * Kmax, (void**)&dunif));
-        IMP_TRY(cudaMemcpyAsync(dunif, uniforms, sizeof(double) * n * n_traj * Kmax, cudaMemcpyHostToDevice, c->stream));
+        IMP_TRY(reserve(10, sizeof(double) * n * ustride, (void**)&dunif));
+        IMP_TRY(cudaMemcpyAsync(dunif, uniforms, sizeof(double) * n * ustride, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (err_out) {
+        IMP_TRY(reserve(11, sizeof(double) * n * n_traj * T, (void**)&derr));
+        IMP_TRY(cudaMemsetAsync(derr, 0, sizeof(double) * n * n_traj * T, c->stream));
     }
     IMP_TRY(cudaMemcpyAsync(dX, X, sizeof(double) * n * T, cudaMemcpyHostToDevice, c->stream));
     IMP_TRY(cudaMemcpyAsync(dmask, missing, (size_t)n * T, cudaMemcpyHostToDevice, c->stream));
     IMP_TRY(cudaMemcpyAsync(dgrid, xgrid, sizeof(double) * G, cudaMemcpyHostToDevice, c->stream));
     IMP_TRY(cudaMemcpyAsync(doff, off.data(), sizeof(int64_t) * T, cudaMemcpyHostToDevice, c->stream));
     IMP_TRY(cudaMemcpyAsync(dchi, chi.data(), sizeof(int) * (T + 1), cudaMemcpyHostToDevice, c->stream));
-    for (int j = 0; j < T; j++) {
-        const Core& k = c->cores[j];
+    for (int p = 0; p < T; p++) {
+        const Core& k = c->cores[pos(p)];
         CoreView v;
         v.p = k.dev; v.ss = 1;
         if (k.orient == ORIENT_LEFT) { v.sa = d; v.sb = (long)d * k.chi_l; } else { v.sb = d; v.sa = (long)d * k.chi_r; }
         v.sc = k.has_label ? (long)d * k.chi_l * k.chi_r : 0;
+        if (backwards) std::swap(v.sa, v.sb);                      // mirrored chain: the links change sides
         const int64_t ne = (int64_t)d * k.chi_l * k.chi_r;
-        slice_core_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(v, d, k.chi_l, k.chi_r, k.has_label ? class_idx : 0, dcores + off[j]);
+        slice_core_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(v, d, chi[p], chi[p + 1], k.has_label ? class_idx : 0, dcores + off[p]);
         c->launches++;
     }
     rc = launch_encode(c, c->basis, d, dgrid, G, dgenc, d);       // grid states, imputation.jl:92-107
@@ -718,6 +840,8 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     P.uniforms = dunif; P.out = dout; P.gr_scratch = dGR; P.p_scratch = dp;
     P.T = T; P.d = d; P.G = G; P.ntraj = n_traj; P.Kmax = Kmax; P.chimax = chimax; P.method = method; P.basis = c->basis;
     P.n = n; P.max_jump = max_jump;
+    P.err = derr; P.get_err = (io && io->get_err) ? 1 : 0; P.max_trials = io ? io->max_trials : 0;
+    P.rej_thr = rejection ? io->rejection_threshold : -1.0; P.ustride = ustride;
     P.debug = c->flag[F_IMPUTE_DEBUG] ? 1 : 0;
     P.dbuf = dbuf ? 1 : 0;
     {
@@ -736,7 +860,14 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     c->launches++;
     IMP_TRY(cudaGetLastError());
     IMP_TRY(cudaMemcpyAsync(out, dout, sizeof(double) * n * n_traj * T, cudaMemcpyDeviceToHost, c->stream));
+    if (err_out) IMP_TRY(cudaMemcpyAsync(err_out, derr, sizeof(double) * n * n_traj * T, cudaMemcpyDeviceToHost, c->stream));
     IMP_TRY(cudaStreamSynchronize(c->stream));
+    if (backwards) {
+        for (int64_t r = 0; r < n * n_traj; r++) {
+            std::reverse(out + r * T, out + (r + 1) * T);
+            if (err_out) std::reverse(err_out + r * T, err_out + (r + 1) * T);
+        }
+    }
     if (P.debug) {
         const auto t_end = std::chrono::steady_clock::now();
         fprintf(stderr, "[impute host] setup %.1f ms, kernel + copy back %.1f ms (grid %d, n %lld)\n",

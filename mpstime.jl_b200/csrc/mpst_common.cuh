@@ -59,6 +59,13 @@ enum {
     L_KRAO_VARIANT,    // reg: NI;  tiles: TN
     L_FWD_PATH,        // 1 factorised + cached environment, 2 factorised, 3 dense
     L_KRAO_REG_MASK,   // bit NI set for every krao_reg_kernel<NI> launched since the mask was last cleared (debug_set)
+    L_GRAD_KR_LAUNCHES,   // launches of bond_grad_kr_kernel / bond_grad_kernel since last cleared (debug_set): bench.py
+    L_GRAD_TILE_LAUNCHES, // names the kernel that did most of the timed work instead of assuming one
+    L_SVD_CALLS,          // cumulative SVD statistics (cleared with debug_set): splits, subspace iterations summed over the
+    L_SVD_ITERS_SUM,      // fast-path splits, splits that needed a second round of iterations, splits that fell back to the
+    L_SVD_ROUND2,         // exact Jacobi, fast-path splits (Gram or subspace)
+    L_SVD_JACOBI,
+    L_SVD_FAST,
     L_COUNT
 };
 
@@ -132,6 +139,9 @@ struct mpst_ctx {
     std::vector<int> env_dir;
     int svd_slot = -1;
     std::vector<int> svd_its, svd_floor;
+    // iteration count proven on the most recently split bond of the same shape: a bond without history of its own starts
+    // from its neighbour's count instead of the conservative default (spectra change slowly along the chain)
+    int svd_hint_m = 0, svd_hint_n = 0, svd_hint_its = 0, svd_hint_floor = 0;
     std::vector<char> svd_nohalf;   // bonds on which the column-scaling shortcut of the subspace iteration broke down once
     // capacities (doubles) of the training buffers: a re-load with the same or a smaller shape reuses them
     size_t cap_X = 0, cap_PHI = 0, cap_phi = 0, cap_env = 0, cap_ones = 0, cap_yw = 0;
@@ -193,8 +203,8 @@ int launch_axpy(mpst_ctx* c, double* B, const double* G, int64_t n, const double
                 double eta, int tsgo);
 int launch_scale_dev(mpst_ctx* c, double* v, int64_t n, const double* norm2_dev);
 int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* missing, int64_t n,
-                 int method, const double* xgrid, int G, const double* uniforms, int n_traj,
-                 double max_jump, double* out);
+                 int method, const double* xgrid, int G, const double* uniforms, int64_t uniforms_per_instance,
+                 int n_traj, const mpst_impute_opts* io, double* out, double* err_out);
 
 // stream-K schedule cache (api.cu)
 SegTable* segtable_find(mpst_ctx* c, const std::vector<int64_t>& key);

@@ -667,6 +667,7 @@ int svd_split_device(mpst_ctx* c, const double* B, int Dl, int Dr, int C, int go
         TRY(launch_sumsq(c, B, (int64_t)Dl * Dr * C, c->scal + 5));
         trace_dev = c->scal + 5;
     }
+    c->last[L_SVD_CALLS]++;
     {   // fast path: subspace iteration + Rayleigh-Ritz (svd_subspace.cu); falls through when not applicable
         bool done = false;
         TRY(svd_subspace_device(c, c->S, ld, m, n, C, chi_max, cutoff, trace_dev, label_core, ortho_core, chi_new, sigma_host, &done));
@@ -680,6 +681,7 @@ int svd_split_device(mpst_ctx* c, const double* B, int Dl, int Dr, int C, int go
     }
     c->last[L_SVD_PATH] = fused ? 4 : 5;
     c->last[L_SVD_ITERS] = 0;
+    c->last[L_SVD_JACOBI]++;
     jac_colnorm_kernel<<<npad, 128, 0, c->stream>>>(c->S, ld, m, c->colnorm);
     jac_sort_trunc_kernel<<<1, 1024, 0, c->stream>>>(c->colnorm, n, npad, chi_max, cutoff, c->perm, c->colnorm + npad, c->iscal);
     jac_gather_kernel<<<2 * c->sm_count, 256, 0, c->stream>>>(c->S, ld, m, n, C, c->perm, c->iscal, label_core, ortho_core);

@@ -566,6 +566,8 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         *chi_new = c->hiscal[0];
         c->last[L_SVD_PATH] = mode == 0 ? 1 : (mode == 1 ? 2 : 3);
         c->last[L_SVD_ITERS] = iters;
+        c->last[L_SVD_ITERS_SUM] += iters;
+        c->last[L_SVD_FAST]++;
         scatter_label_kernel<<<2 * c->sm_count, 256, 0, c->stream>>>(Uk, m, m / C, c->iscal, label_core);
         c->launches++;
         CUDA_TRY(c, cudaGetLastError());
@@ -649,7 +651,10 @@ restart:
         // bond's floor for good, so every level is tried at most once per bond
         const int slot = (c->svd_slot >= 0 && c->svd_slot < (int)c->svd_its.size()) ? c->svd_slot : -1;
         int first = c->flag[F_SVD_IT] > 0 ? c->flag[F_SVD_IT] : (p >= 2 * k ? 5 : 7);
+        const bool hinted = slot >= 0 && c->svd_its[slot] == 0 && c->flag[F_SVD_IT] <= 0 && c->svd_hint_its > 0 &&
+                            c->svd_hint_m == m && c->svd_hint_n == n;
         if (slot >= 0 && c->svd_its[slot] > 0 && c->flag[F_SVD_IT] <= 0) first = c->svd_its[slot];
+        else if (hinted) first = std::max(c->svd_hint_its, c->svd_floor[slot]);
         const int niter = round == 0 ? first : 3;
         for (int it = 0; it < niter; it++) {
             TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, Qa, n, Za, m));            // Z = M Q
@@ -711,12 +716,21 @@ restart:
                 // passed at `first`: try one fewer next time if that level has not failed before and the margin is there
                 if (res <= 1.5e-14 && first - 1 >= std::max(3, c->svd_floor[slot])) c->svd_its[slot] = first - 1;
                 else c->svd_its[slot] = first;
+                // ... and the next bond of this shape without history starts one below what just passed with margin,
+                // unless that level already failed somewhere along the chain
+                c->svd_hint_m = m; c->svd_hint_n = n;
+                c->svd_hint_its = (res <= 1.5e-14 && first - 1 >= std::max(3, c->svd_hint_floor)) ? first - 1 : first;
             } else if (round == 0) {
                 c->svd_floor[slot] = first + 1;
                 c->svd_its[slot] = first + 1;
+                if (c->svd_hint_m == m && c->svd_hint_n == n) {
+                    c->svd_hint_floor = std::max(c->svd_hint_floor, first + 1);
+                    c->svd_hint_its = std::max(c->svd_hint_its, first + 1);
+                }
             }
         }
         if (res <= 5e-14) return finish("subspace", iters_done, res);
+        if (round == 0) c->last[L_SVD_ROUND2]++;
         if (res > (round == 0 ? 1e-5 : 1e-10)) {                                   // spectrum too flat: full Jacobi
             if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d residual %.2e after %d its -> full Jacobi\n", m, n, res, iters_done);
             return MPST_OK;

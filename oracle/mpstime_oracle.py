@@ -745,36 +745,109 @@ def cumtrapz_even_fast(xs, y):
     return (xs[1] - xs[0]) * 0.5 * c
 
 
-def impute_series(class_cores, x_scaled, missing, grid, grid_enc, d, basis="legendre_no_norm",
-                  method="median", uniforms=None, max_jump=None):
-    """impute_median / impute_mean / impute_mode / impute_ITS (MPS_methods.jl:201-347) on one
+def weighted_median(v, w):
+    """StatsBase 0.34.4 `median(v, pweights(w))` = `quantile(v, w, 0.5)` (un-vendored; published algorithm restated):
+    drop zero weights, sort the (value, weight) pairs, h = p*(sum(w) - w_1) + w_1 with w_1 the weight of the smallest
+    value, walk the cumulative weight S_k until S_k > h and interpolate linearly between the last two values."""
+    v = np.asarray(v, dtype=np.float64)
+    w = np.asarray(w, dtype=np.float64)
+    nz = w != 0
+    order = np.lexsort((w[nz], v[nz]))                      # tuples sort by value, then weight
+    vs, ws = v[nz][order], w[nz][order]
+    wsum = float(np.sum(w))
+    h = 0.5 * (wsum - ws[0]) + ws[0]
+    S = np.cumsum(ws)
+    k = int(np.searchsorted(S, h, side="right"))            # first k with S_k > h
+    if k >= len(vs):
+        return float(vs[-1])
+    Sk_old = S[k - 1] if k > 0 else 0.0
+    vk_old = vs[k - 1] if k > 0 else 0.0
+    return float(vk_old + (h - Sk_old) / (S[k] - Sk_old) * (vs[k] - vk_old))
+
+
+def orthogonalize_to_last(cond):
+    """ITensors orthogonalize!(mps, length(mps)) (MPS_methods.jl:115, impute_order=:backwards): QR sweep left -> right."""
+    cond = [A.copy() for A in cond]
+    for k in range(len(cond) - 1):
+        A = cond[k]
+        a, s, b = A.shape
+        Qm, Rm = np.linalg.qr(A.reshape(a * s, b))
+        r = Qm.shape[1]
+        cond[k] = Qm.reshape(a, s, r)
+        cond[k + 1] = np.einsum("rb,bsy->rsy", Rm, cond[k + 1])
+    return cond
+
+
+def impute_series_ex(class_cores, x_scaled, missing, grid, grid_enc, d, basis="legendre_no_norm",
+                     method="median", uniforms=None, max_jump=None, impute_order="forwards", get_err=False,
+                     rejection_threshold=None, max_trials=10):
+    """impute_median / impute_mean / impute_mode / impute_ITS (MPS_methods.jl:201-347) -> impute_at! (:93-180) on one
     series already in the encoding range with the missing entries filled (imputation.jl:290-291).
-    Returns (x_out (T,), grid_index (K,) or None)."""
+    `impute_order`: "forwards" (orthogonalize!(mps, 1), walk first -> last missing site) or "backwards" (:102-118).
+    `get_err`: the method's error bar per imputed site -- WMAD for the median (get_wmad, sampling_utils.jl:192-196),
+    the standard deviation for the mean (get_std, :89-97), the WMAD for ITS with rejection (:295-311), 0 otherwise.
+    `rejection_threshold` (ITS): None = :none; else up to `max_trials` draws per site, accepted when
+    |x - median| < threshold * WMAD (the last draw stands if none is accepted); `uniforms` is then the flat stream of
+    rand(rng) values consumed in order (the reference shares one MersenneTwister over sites and trajectories).
+    Returns (x_out (T,), grid_index (K,), errs (T,), draws_used)."""
     T = len(class_cores)
     missing = sorted(int(m) for m in missing)
     x_out = np.array(x_scaled, dtype=np.float64).copy()
+    errs = np.zeros(T)
     phi_ts = encode(x_out, d, basis)
     cond = precondition(class_cores, phi_ts, missing)
-    cond = orthogonalize_to_first(cond)
-    A = cond[0][0]                                            # (d, chi)
     K = len(missing)
+    fwd = impute_order == "forwards"
+    if fwd:
+        cond = orthogonalize_to_first(cond)
+        A = cond[0][0]                                        # (d, chi)
+        order = list(range(K))
+        x_prev = x_out[missing[0] - 1] if missing[0] > 0 else None            # MPS_methods.jl:136-138
+    elif impute_order == "backwards":
+        cond = orthogonalize_to_last(cond)
+        A = cond[-1][:, :, 0].T                               # (d, chi): site first, link to the rest second
+        order = list(range(K - 1, -1, -1))
+        x_prev = x_out[missing[-1] + 1] if missing[-1] + 1 < T else None      # :139-141
+    else:
+        raise ValueError('impute_order must be either "forwards" or "backwards"')
     idxs = np.zeros(K, dtype=np.int64)
     dxm = float(np.mean(np.abs(np.diff(grid))))
-    x_prev = x_out[missing[0] - 1] if missing[0] > 0 else None        # MPS_methods.jl:136-144
-    for k in range(K):
+    ucur = 0
+    for ii, k in enumerate(order):
         rdm = A @ A.conj().T                                  # :152
         p = cond_probs(rdm, grid_enc)
+        err = 0.0
         if method == "median":                                # sampling_utils.jl:162-199
             cdf = cumtrapz_even_fast(grid, p)
             Z = cdf[-1]
             g = int(np.argmin(np.abs(cdf / Z - 0.5)))
             xv, st = grid[g], grid_enc[g] / np.sqrt(Z)
-        elif method == "ITS":                                 # :263-316 (no rejection)
+            if get_err:
+                err = weighted_median(np.abs(grid - xv), p / Z)
+        elif method == "ITS" and rejection_threshold is None:   # :263-290 (no rejection)
             cdf = cumtrapz_even_fast(grid, p)
             cdf = cdf / cdf[-1]
             Z = cdf[-1]
-            g = int(np.argmin(np.abs(cdf / Z - uniforms[k])))
+            u = uniforms[ucur]
+            ucur += 1
+            g = int(np.argmin(np.abs(cdf / Z - u)))
             xv, st = grid[g], grid_enc[g] / np.sqrt(Z)
+        elif method == "ITS":                                 # :291-311 (rejection by WMAD)
+            cdf = cumtrapz_even_fast(grid, p)
+            Zr = cdf[-1]
+            cdf = cdf / Zr
+            gm = int(np.argmin(np.abs(cdf - 0.5)))
+            wmad = weighted_median(np.abs(grid - grid[gm]), p / Zr)
+            Z = cdf[-1]
+            g = gm
+            for _ in range(max_trials):
+                u = uniforms[ucur]
+                ucur += 1
+                g = int(np.argmin(np.abs(cdf / Z - u)))
+                if abs(grid[g] - grid[gm]) < rejection_threshold * wmad:
+                    break
+            xv, st = grid[g], grid_enc[g] / np.sqrt(Z)
+            err = wmad
         elif method == "mode":                                # :104-158
             if x_prev is None or max_jump is None:
                 g = int(np.argmax(p))
@@ -788,14 +861,28 @@ def impute_series(class_cores, x_scaled, missing, grid, grid_enc, d, basis="lege
             xv = float(np.sum(grid * p) * dxm / Z)
             st = encode(np.array(xv), d, basis) / np.sqrt(Z)
             g = -1
+            if get_err:
+                err = float(np.sqrt(np.sum((grid - xv) ** 2 * p) * dxm / Z))
         else:
             raise ValueError(method)
         idxs[k] = g
         x_out[missing[k]] = xv
+        errs[missing[k]] = err
         x_prev = xv
-        if k != K - 1:                                        # MPS_methods.jl:161-168, norm=false
+        if ii != K - 1:                                       # MPS_methods.jl:161-168, norm=false
             v = st.conj() @ A
-            A = np.einsum("a,asb->sb", v, cond[k + 1])
+            if fwd:
+                A = np.einsum("a,asb->sb", v, cond[k + 1])
+            else:
+                A = np.einsum("asb,b->sa", cond[k - 1], v)
+    return x_out, idxs, errs, ucur
+
+
+def impute_series(class_cores, x_scaled, missing, grid, grid_enc, d, basis="legendre_no_norm",
+                  method="median", uniforms=None, max_jump=None):
+    """Forward-order imputation without error bars: (x_out (T,), grid_index (K,)).  See impute_series_ex."""
+    x_out, idxs, _, _ = impute_series_ex(class_cores, x_scaled, missing, grid, grid_enc, d, basis, method, uniforms,
+                                         max_jump)
     return x_out, idxs
 
 

@@ -210,3 +210,32 @@ def test_reference_trained_mps_pins_layout_norm_and_classification(oracle):
     assert np.all(np.diff(np.sqrt(np.diag(Gm))) <= 1e-12)              # sorted descending as LAPACK returns them
     # truncate! with cutoff 1e-10 kept them all: the discarded tail is below the cutoff only if nothing smaller exists
     assert sig[-1] ** 2 / np.sum(sig ** 2) > 1e-10
+
+
+def test_weighted_median_and_backwards_imputation(oracle):
+    """Self-checks of the a18 restatements: StatsBase's weighted quantile on hand-computable cases, and
+    impute_order=:backwards == the forward walk on the mirrored chain (an independent formulation: the oracle walks
+    right to left after a left-to-right QR sweep; the mirrored chain uses the forward code)."""
+    assert oracle.weighted_median([1.0, 2.0, 3.0], [1.0, 1.0, 1.0]) == 2.0
+    assert abs(oracle.weighted_median([3.0, 1.0, 2.0], [0.2, 0.2, 0.6]) - 5.0 / 3.0) < 1e-15    # h = 0.6: 1 + (0.6-0.2)/0.6 * (2-1)
+    assert abs(oracle.weighted_median([0.0, 1.0], [1.0, 1.0]) - 0.5) < 1e-15                     # h = 1.5: halfway 0 -> 1
+    assert oracle.weighted_median([5.0, 0.0, 7.0], [0.0, 1.0, 0.0]) == 0.0                        # zero weights dropped
+    N, T, d, C = 60, 9, 3, 2
+    X, y = oracle.synthetic_two_class(N, T, seed=4)
+    Xs, _ = oracle.transform_train_data(X.T)
+    phi, ys, order, counts, classes = oracle.encode_dataset(Xs, y, d)
+    cores = oracle.fit_sweeps(oracle.random_start_mps(T, d, 3, C, seed=2), phi, counts, nsweeps=2, chi_max=6, eta=0.05)
+    cls = oracle.expand_label_index(cores)[0]
+    mirrored = [A.transpose(2, 1, 0).copy() for A in reversed(cls)]
+    grid = oracle.make_grid((-1.0, 1.0), 2e-3)
+    genc = oracle.encode(grid, d)
+    x = Xs[:, 5].copy()
+    for ms in ([2, 3, 4], [0, 1], [6, 7, 8], [1, 4, 6]):
+        for method in ("median", "mean", "mode"):
+            a, _, ea, _ = oracle.impute_series_ex(cls, x, ms, grid, genc, d, method=method, impute_order="backwards", get_err=True)
+            b, _, eb, _ = oracle.impute_series_ex(mirrored, x[::-1], [T - 1 - m for m in ms], grid, genc, d, method=method, get_err=True)
+            assert np.abs(a - b[::-1]).max() < 1e-9 and np.abs(ea - eb[::-1]).max() < 1e-9, (ms, method)
+    # forwards, default arguments: unchanged wrapper
+    a, ia = oracle.impute_series(cls, x, [2, 3, 4], grid, genc, d)
+    b, ib, _, _ = oracle.impute_series_ex(cls, x, [2, 3, 4], grid, genc, d)
+    assert np.array_equal(a, b) and np.array_equal(ia, ib)
