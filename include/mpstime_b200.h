@@ -136,6 +136,16 @@ int mpst_sweep_bonds(mpst_ctx* ctx, const mpst_train_opts* opts, int n_bonds, in
  *      class index, first maximum of |yhat|^2). ------------------------------------------- */
 int mpst_overlaps(mpst_ctx* ctx, const double* X_or_phi, int64_t n, double* yhat, int64_t* argmax);
 
+/* ---- per-sweep evaluation on the device: MSE_loss_acc / MSE_loss_acc_conf (summary.jl:33-114), which fitMPS runs on
+ *      the train and test sets after every sweep when log_level > 0 (RealRealHighDimension.jl:813-845).  Runs the K7
+ *      chain and reduces on the device; only 3 + C*C numbers come back.  X_or_phi as in mpst_overlaps with
+ *      label_idx[i] the 0-based class index of sample i; X_or_phi == NULL evaluates the training set already resident
+ *      on the device (labels = its sorted class ranges; n and label_idx ignored; on a sharded run: this rank's shard).
+ *      sums[3] = { sum_i 0.5*|yhat_i - onehot_i|^2, sum_i -log|yhat_i,label|^2, number correct } (the caller divides by
+ *      the global sample count); conf: C x C row-major counts conf[true][predicted] (NULL to skip). ------------------ */
+int mpst_eval_metrics(mpst_ctx* ctx, const double* X_or_phi, int64_t n, const int64_t* label_idx, double* sums,
+                      int64_t* conf);
+
 /* ---- K8: MPS_impute batch (Imputation/imputation.jl:264-410 get_predictions ->
  *      MPS_methods.jl:42-180 precondition + impute_at! -> sampling_utils.jl:64-316).
  *      Uses the class_idx slice of the context's current MPS (expand_label_index,

@@ -48,6 +48,7 @@ SIGNATURES = {
     "mpst_sweep": (C.c_int, [C.c_void_p, C.POINTER(TrainOpts), C.c_int, c_double_p, c_double_p, c_i32_p]),
     "mpst_sweep_bonds": (C.c_int, [C.c_void_p, C.POINTER(TrainOpts), C.c_int, C.c_int, c_double_p, c_double_p, c_i32_p]),
     "mpst_overlaps": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_i64_p]),
+    "mpst_eval_metrics": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_i64_p, c_double_p, c_i64_p]),
     "mpst_impute_batch": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_u8_p, C.c_int64, C.c_int, c_double_p,
                                     C.c_int, c_double_p, C.c_int, C.c_double, c_double_p]),
     "mpst_impute_batch_ex": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_u8_p, C.c_int64, C.c_int, c_double_p,

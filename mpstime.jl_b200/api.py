@@ -122,19 +122,24 @@ def _train_opts(opts):
                      chi_max=opts.chi_max, eta=opts.eta, cutoff=opts.cutoff)
 
 
-def _eval_set(ctx, X_scaled, label_idx, C):
-    """MSE_loss_acc(_conf) (summary.jl:33-114) from device overlaps."""
-    yh, am = ctx.overlaps(X_TxN=X_scaled)
-    n = yh.shape[0]
-    onehot = np.zeros_like(yh)
-    onehot[np.arange(n), label_idx] = 1.0
-    mse = float(np.mean(0.5 * np.sum((yh - onehot) ** 2, axis=1)))
-    kld = float(np.mean(-np.log(yh[np.arange(n), label_idx] ** 2)))
-    pred = np.argmax(np.abs(yh), axis=1)
-    acc = float(np.mean(pred == label_idx))
-    conf = np.zeros((C, C), dtype=np.int64)
-    np.add.at(conf, (label_idx, pred), 1)
-    return mse, kld, acc, conf
+def _eval_set(ctx, X_scaled=None, label_idx=None, resident=False):
+    """MSE_loss_acc(_conf) (summary.jl:33-114), reduced on the device (mpst_eval_metrics): only 3 + C*C numbers come
+    back per set and sweep.  resident=True evaluates the training set already in HBM (on a sharded run each rank
+    evaluates its shard and the sums are all-reduced)."""
+    if resident:
+        sums, conf, n = ctx.eval_metrics()
+        rank, world = _dist.rank_world()
+        if world > 1:
+            import torch
+            import torch.distributed as td
+            t = torch.tensor(np.concatenate([sums, conf.reshape(-1).astype(np.float64), [float(n)]]),
+                             dtype=torch.float64, device=f"cuda:{ctx.device}")
+            td.all_reduce(t)
+            v = t.cpu().numpy()
+            sums, conf, n = v[:3], np.rint(v[3:-1]).astype(np.int64).reshape(conf.shape), int(round(v[-1]))
+    else:
+        sums, conf, n = ctx.eval_metrics(X_TxN=X_scaled, labels=label_idx)
+    return float(sums[0] / n), float(sums[1] / n), float(sums[2] / n), conf
 
 
 def fitMPS(X_train, y_train=None, X_test=None, y_test=None, opts: Optional[MPSOptions] = None, W=None,
@@ -188,11 +193,11 @@ def fitMPS(X_train, y_train=None, X_test=None, y_test=None, opts: Optional[MPSOp
     def log(elapsed):
         if opts.log_level <= 0:
             return None
-        mse, kld, acc, _ = _eval_set(ctx, Xs_sorted, tr_idx, C)
+        mse, kld, acc, _ = _eval_set(ctx, resident=True)
         info["train_loss"].append(mse); info["train_acc"].append(acc)
         info["time_taken"].append(elapsed); info["train_KL_div"].append(kld)
         if has_test:
-            mse_t, kld_t, acc_t, conf = _eval_set(ctx, test_states.X_scaled, te_idx, C)
+            mse_t, kld_t, acc_t, conf = _eval_set(ctx, test_states.X_scaled, te_idx)
             info["test_loss"].append(mse_t); info["test_acc"].append(acc_t)
             info["test_KL_div"].append(kld_t); info["test_conf"].append(conf)
         if opts.verbosity > -1:

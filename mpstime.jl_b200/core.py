@@ -203,6 +203,27 @@ class Context:
         self._chk(self.lib.mpst_overlaps(self.h, _dp(data), n, _dp(yh), am.ctypes.data_as(c_i64_p)))
         return yh, am
 
+    def eval_metrics(self, X_TxN=None, phi_NTd=None, labels=None):
+        """MSE_loss_acc_conf on the device (summary.jl:60-114).  No data argument: the resident training set (this
+        rank's shard).  Returns (sums [mse_sum, kld_sum, n_correct], conf (C, C) int64, n)."""
+        sums = np.zeros(3)
+        conf = np.zeros((self.C, self.C), dtype=np.int64)
+        if X_TxN is None and phi_NTd is None:
+            self._chk(self.lib.mpst_eval_metrics(self.h, None, 0, None, _dp(sums), conf.ctypes.data_as(c_i64_p)))
+            return sums, conf, int(conf.sum())
+        if phi_NTd is not None:
+            data = _f64(phi_NTd)
+            n = data.shape[0]
+        else:
+            X = np.asarray(X_TxN, dtype=np.float64)
+            n = X.shape[1]
+            data = np.ascontiguousarray(X.T)
+        lab = np.ascontiguousarray(labels, dtype=np.int64)
+        assert lab.shape == (n,)
+        self._chk(self.lib.mpst_eval_metrics(self.h, _dp(data), n, lab.ctypes.data_as(c_i64_p), _dp(sums),
+                                             conf.ctypes.data_as(c_i64_p)))
+        return sums, conf, n
+
     # ---- K8 ---------------------------------------------------------------------------------
     def impute_batch(self, class_idx, X_TxN, missing_TxN, grid, method="median", uniforms=None, n_traj=1,
                      max_jump=-1.0, impute_order="forwards", get_err=False, rejection_threshold=None, max_trials=10,

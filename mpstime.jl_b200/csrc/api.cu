@@ -21,6 +21,9 @@ int launch_scale_const(mpst_ctx* c, double* v, int64_t n, double f);
 int launch_transpose(mpst_ctx* c, const double* in, double* out, int64_t rows, int64_t cols, int64_t ldo);
 int launch_fill(mpst_ctx* c, double* v, int64_t n, double val);
 int launch_argmax(mpst_ctx* c, const double* yhat, int64_t Npad, int64_t n, int C, double* out_yhat, int64_t* out_arg);
+int launch_metrics(mpst_ctx* c, const double* y, int64_t ldy, int64_t n, int C, const int64_t* labels_dev,
+                   const int64_t* class_off_dev, int64_t i0, double* p_mse, double* p_kld, double* p_acc, int nblocks,
+                   unsigned long long* conf_dev);
 int launch_bond_grad(mpst_ctx* c, const double* xl, const double* xr, const double* L, const double* R, int d,
                      int chi_l, int chi_r, const int64_t* cls_begin, const int64_t* cls_end, int ncls, double* G);
 int launch_bond_grad_kr(mpst_ctx* c, const double* xl, const double* xr, const double* L, const double* R, int d,
@@ -211,7 +214,7 @@ const FlagDef kFlags[F_COUNT] = {
     {"SVD_DEBUG", 0, true}, {"SVD_SKIP", 0, false}, {"SVD_FIXED", 0, false}, {"SVD_FULL", 0, true},
     {"SVD_PB64", 0, true}, {"SVD_LEGACY", 0, true}, {"SVD_NOSUB", 0, true}, {"SVD_OVS", 0, false},
     {"SVD_NOHALF", 0, true}, {"SVD_HALF_FROM", 1, false}, {"SVD_IT", 0, false}, {"SVD_NOGRAPH", 0, true},
-    {"GRAD_KC", 0, false},
+    {"GRAD_KC", 0, false}, {"IMPUTE_NOSERIES", 0, true}, {"IMPUTE_FULLSYM", 0, true},
 };
 const char* kLast[L_COUNT] = {"svd_path", "svd_iters", "svd_restarts", "grad_kernel", "grad_variant", "krao_kernel",
                               "krao_variant", "fwd_path", "krao_reg_mask", "grad_kr_launches", "grad_tile_launches", "svd_calls",
@@ -317,7 +320,7 @@ int mpst_destroy(mpst_ctx* c) {
     auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(c->B); fr(c->G); fr(c->Z); fr(c->part); fr(c->red); fr(c->scal); fr(c->S); fr(c->gpart); fr(c->wbuf);
     fr(c->colnorm); fr(c->tmp); fr(c->meta); fr(c->sub); fr(c->gws);
-    for (int i = 0; i < 12; i++) if (c->imp_ptr[i]) cudaFree(c->imp_ptr[i]);
+    for (int i = 0; i < 16; i++) if (c->imp_ptr[i]) cudaFree(c->imp_ptr[i]);
     if (c->hmeta) cudaFreeHost(c->hmeta);
     if (c->perm) cudaFree(c->perm);
     if (c->flags) cudaFree(c->flags);
@@ -913,11 +916,14 @@ int64_t mpst_debug_get(mpst_ctx* c, const char* name) {
     return -1;
 }
 
-int mpst_overlaps(mpst_ctx* c, const double* X_or_phi, int64_t n, double* yhat, int64_t* argmax) {
-    if (!c || !X_or_phi || c->T == 0 || n < 0 || (!yhat && !argmax)) return MPST_E_INVALID;
+// Shared body of mpst_overlaps and mpst_eval_metrics: K6 chains from both ends + label-site contraction per batch of
+// samples.  src == nullptr: the training set already resident on the device (x or phi mode).
+static int overlaps_impl(mpst_ctx* c, const double* X_or_phi, int64_t n, double* yhat, int64_t* argmax,
+                         const int64_t* labels, bool want_metrics, double* metrics, int64_t* conf) {
     if (n == 0) return MPST_OK;
     CUDA_TRY(c, cudaSetDevice(c->device));
     const int T = c->T, d = c->d, C = c->C;
+    const bool resident = X_or_phi == nullptr;
     int pos = -1;
     for (int j = 0; j < T; j++) {
         if (!c->cores[j].dev) { c->err = "overlaps: cores not set"; return MPST_E_INVALID; }
@@ -931,14 +937,17 @@ int mpst_overlaps(mpst_ctx* c, const double* X_or_phi, int64_t n, double* yhat, 
     const int64_t BS = std::min<int64_t>(round_up(n, MPST_TILE), 1 << 16);       // samples per batch
     const int64_t BP = BS + MPST_TILE;
     const int width = c->have_phi ? d : 1;
-    // buffers: xin [T][BP][width], phi [BP][d], envA/envB/envR [BP][chimax], Z [BP][chimax*C], y [C][BP], outputs
-    const size_t need = (size_t)T * BP * width + (size_t)BP * d + 3 * (size_t)BP * chimax + (size_t)BP * chimax * C +
-                        (size_t)C * BP + (size_t)BP * C + 2 * BP + 64;
+    const int64_t nbatch = (n + BS - 1) / BS;
+    const int64_t mblocks = (BS + 255) / 256;                                     // metric partials per batch
+    // buffers: xin [T][BP][width] (host source only), phi [BP][d], envA/envB/envR [BP][chimax], Z [BP][chimax*C],
+    // y [C][BP], outputs, labels, metric partials [3][nbatch*mblocks], confusion counts
+    const size_t need = (resident ? 0 : (size_t)T * BP * width) + (size_t)BP * d + 3 * (size_t)BP * chimax + (size_t)BP * chimax * C +
+                        (size_t)C * BP + (size_t)BP * C + 3 * BP + 3 * (size_t)(nbatch * mblocks) + (size_t)C * C + 64;
     double* buf = nullptr;
     CUDA_TRY(c, cudaMalloc(&buf, need * sizeof(double)));
     CUDA_TRY(c, cudaMemsetAsync(buf, 0, need * sizeof(double), c->stream));
     double* xin = buf;
-    double* ph = xin + (size_t)T * BP * width;
+    double* ph = xin + (resident ? 0 : (size_t)T * BP * width);
     double* eA = ph + (size_t)BP * d;
     double* eB = eA + (size_t)BP * chimax;
     double* eR = eB + (size_t)BP * chimax;
@@ -947,12 +956,18 @@ int mpst_overlaps(mpst_ctx* c, const double* X_or_phi, int64_t n, double* yhat, 
     double* oy = y + (size_t)C * BP;
     int64_t* oarg = reinterpret_cast<int64_t*>(oy + (size_t)BP * C);
     double* ones = oy + (size_t)BP * C + BP;
+    int64_t* dlab = reinterpret_cast<int64_t*>(ones + BP);
+    double* mpart = ones + 2 * BP;
+    unsigned long long* dconf = reinterpret_cast<unsigned long long*>(mpart + 3 * (size_t)(nbatch * mblocks));
     if (launch_fill(c, ones, BP, 1.0) != MPST_OK) { cudaFree(buf); return MPST_E_CUDA; }
     int rc = MPST_OK;
     auto body = [&]() -> int {
-        for (int64_t i0 = 0; i0 < n; i0 += BS) {
+        int64_t ib = 0;
+        for (int64_t i0 = 0; i0 < n; i0 += BS, ib++) {
             const int64_t nn = std::min<int64_t>(BS, n - i0);
-            if (c->have_phi) {
+            if (resident) {
+                // nothing to stage: the chain reads the resident site-major series / phi directly
+            } else if (c->have_phi) {
                 for (int j = 0; j < T; j++)
                     CUDA_TRY(c, cudaMemcpy2DAsync(xin + (size_t)j * BP * d, sizeof(double) * d, X_or_phi + ((size_t)i0 * T + j) * d,
                                                   sizeof(double) * d * T, sizeof(double) * d, nn, cudaMemcpyHostToDevice, c->stream));
@@ -962,8 +977,11 @@ int mpst_overlaps(mpst_ctx* c, const double* X_or_phi, int64_t n, double* yhat, 
                 TRY(launch_transpose(c, c->tmp, xin, nn, T, BP));
             }
             auto phi_of = [&](int j, const double** out) -> int {
-                if (c->have_phi) { *out = xin + (size_t)j * BP * d; return MPST_OK; }
-                TRY(launch_encode(c, c->basis, d, xin + (size_t)j * BP, nn, ph, d));
+                if (c->have_phi) {
+                    *out = resident ? c->PHI + ((size_t)j * c->Npad + i0) * d : xin + (size_t)j * BP * d;
+                    return MPST_OK;
+                }
+                TRY(launch_encode(c, c->basis, d, resident ? c->X + (size_t)j * c->Npad + i0 : xin + (size_t)j * BP, nn, ph, d));
                 *out = ph;
                 return MPST_OK;
             };
@@ -1004,10 +1022,25 @@ int mpst_overlaps(mpst_ctx* c, const double* X_or_phi, int64_t n, double* yhat, 
             TRY(launch_krao_gemm(c, p, LEp, kp.dev, Z, nn, d, chiL, kp.chi_r * C, (int64_t)d * kp.chi_l, (int64_t)kp.chi_r * C));
             for (int cls = 0; cls < C; cls++)
                 TRY(launch_rowdot(c, Z + (size_t)cls * kp.chi_r, (int64_t)kp.chi_r * C, Er, chiR, 0, nn, kp.chi_r, y + (size_t)cls * BP));
-            TRY(launch_argmax(c, y, BP, nn, C, oy, oarg));
+            if (want_metrics) {
+                // summary.jl:33-114 on the device: per-sample quadratic cost, -log|yhat_label|^2, argmax |yhat|, confusion
+                if (labels) CUDA_TRY(c, cudaMemcpyAsync(dlab, labels + i0, sizeof(int64_t) * nn, cudaMemcpyHostToDevice, c->stream));
+                TRY(launch_metrics(c, y, BP, nn, C, labels ? dlab : nullptr, reinterpret_cast<const int64_t*>(c->meta), i0,
+                                   mpart + ib * mblocks, mpart + (nbatch + ib) * mblocks, mpart + (2 * nbatch + ib) * mblocks, (int)mblocks, dconf));
+            }
+            if (yhat || argmax) TRY(launch_argmax(c, y, BP, nn, C, oy, oarg));
             if (yhat) CUDA_TRY(c, cudaMemcpyAsync(yhat + (size_t)i0 * C, oy, sizeof(double) * nn * C, cudaMemcpyDeviceToHost, c->stream));
             if (argmax) CUDA_TRY(c, cudaMemcpyAsync(argmax + i0, oarg, sizeof(int64_t) * nn, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        }
+        if (want_metrics) {
+            for (int q = 0; q < 3; q++) TRY(launch_final_sum(c, mpart + (size_t)q * nbatch * mblocks, (int)(nbatch * mblocks), c->scal + 12 + q));
+            CUDA_TRY(c, cudaMemcpyAsync(c->hscal + 12, c->scal + 12, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            std::vector<unsigned long long> hc((size_t)C * C);
+            CUDA_TRY(c, cudaMemcpyAsync(hc.data(), dconf, sizeof(unsigned long long) * C * C, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            for (int q = 0; q < 3; q++) metrics[q] = c->hscal[12 + q];
+            if (conf) for (int e = 0; e < C * C; e++) conf[e] = (int64_t)hc[e];
         }
         return MPST_OK;
     };
@@ -1015,6 +1048,28 @@ int mpst_overlaps(mpst_ctx* c, const double* X_or_phi, int64_t n, double* yhat, 
     cudaStreamSynchronize(c->stream);
     cudaFree(buf);
     return rc;
+}
+
+int mpst_overlaps(mpst_ctx* c, const double* X_or_phi, int64_t n, double* yhat, int64_t* argmax) {
+    if (!c || !X_or_phi || c->T == 0 || n < 0 || (!yhat && !argmax)) return MPST_E_INVALID;
+    return overlaps_impl(c, X_or_phi, n, yhat, argmax, nullptr, false, nullptr, nullptr);
+}
+
+int mpst_eval_metrics(mpst_ctx* c, const double* X_or_phi, int64_t n, const int64_t* label_idx, double* sums,
+                      int64_t* conf) {
+    if (!c || c->T == 0 || n < 0 || !sums) return MPST_E_INVALID;
+    sums[0] = sums[1] = sums[2] = 0.0;
+    if (conf) for (int e = 0; e < c->C * c->C; e++) conf[e] = 0;
+    if (!X_or_phi) {                                   // the resident training set: labels are the sorted class ranges
+        if (c->N == 0 || (!c->X && !c->PHI)) { c->err = "eval_metrics: no training set loaded"; return MPST_E_INVALID; }
+        n = c->N;
+        int64_t* coff; double* den;
+        TRY(upload_class_meta(c, MPST_LOSS_KLD, 0, &coff, &den));
+        return overlaps_impl(c, nullptr, n, nullptr, nullptr, nullptr, true, sums, conf);
+    }
+    if (!label_idx) { c->err = "eval_metrics: labels needed for a host data set"; return MPST_E_INVALID; }
+    for (int64_t i = 0; i < n; i++) if (label_idx[i] < 0 || label_idx[i] >= c->C) { c->err = "eval_metrics: label out of range"; return MPST_E_INVALID; }
+    return overlaps_impl(c, X_or_phi, n, nullptr, nullptr, label_idx, true, sums, conf);
 }
 
 int mpst_bond_loss_grad(mpst_ctx* c, const double* B, const double* L, const double* R, const double* xl,

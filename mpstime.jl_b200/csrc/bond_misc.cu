@@ -206,6 +206,39 @@ __global__ void argmax_kernel(const double* __restrict__ yhat, int64_t Npad, int
     }
     out_arg[i] = best;
 }
+// Per-sample terms of MSE_loss_acc(_conf) (summary.jl:33-114) from the overlaps y[c][i]: quadratic cost
+// 0.5 sum_c (y_c - delta)^2, KL term -log(y_label^2), correct = (argmax_c |y_c| == label), confusion[label][pred]++.
+// Block partial sums (fixed order -> deterministic); counts through integer atomics (exact in any order).
+// labels == nullptr: sample i0 + i belongs to the class whose sorted range [class_off[c], class_off[c+1]) contains it.
+__global__ void __launch_bounds__(256)
+metrics_kernel(const double* __restrict__ y, int64_t ldy, int64_t n, int C, const int64_t* __restrict__ labels,
+               const int64_t* __restrict__ class_off, int64_t i0, double* __restrict__ p_mse, double* __restrict__ p_kld,
+               double* __restrict__ p_acc, unsigned long long* __restrict__ conf) {
+    __shared__ double sh[8];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double mse = 0.0, kld = 0.0, acc = 0.0;
+    if (i < n) {
+        int li;
+        if (labels) li = (int)labels[i];
+        else { li = 0; while (li + 1 < C && i0 + i >= class_off[li + 1]) li++; }
+        int pred = 0;
+        double best = -1.0;
+        for (int c = 0; c < C; c++) {
+            const double v = y[(int64_t)c * ldy + i];
+            const double df = v - (c == li ? 1.0 : 0.0);
+            mse += df * df;
+            if (fabs(v) > best) { best = fabs(v); pred = c; }
+            if (c == li) kld = -log(v * v);
+        }
+        mse *= 0.5;
+        acc = pred == li ? 1.0 : 0.0;
+        atomicAdd(&conf[(size_t)li * C + pred], 1ull);
+    }
+    mse = block_sum(mse, sh);
+    kld = block_sum(kld, sh);
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) { p_mse[blockIdx.x] = mse; p_kld[blockIdx.x] = kld; p_acc[blockIdx.x] = acc; }
+}
 }  // namespace
 
 static inline unsigned grid_for(int64_t n, int threads = 256, int64_t cap = 148 * 16) {
@@ -319,6 +352,16 @@ int launch_fill(mpst_ctx* c, double* v, int64_t n, double val) {
 
 int launch_argmax(mpst_ctx* c, const double* yhat, int64_t Npad, int64_t n, int C, double* out_yhat, int64_t* out_arg) {
     argmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(yhat, Npad, n, C, out_yhat, out_arg);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return MPST_OK;
+}
+
+int launch_metrics(mpst_ctx* c, const double* y, int64_t ldy, int64_t n, int C, const int64_t* labels_dev,
+                   const int64_t* class_off_dev, int64_t i0, double* p_mse, double* p_kld, double* p_acc, int nblocks,
+                   unsigned long long* conf_dev) {
+    // every one of the `nblocks` partial slots is written (blocks past n contribute zeros)
+    metrics_kernel<<<nblocks, 256, 0, c->stream>>>(y, ldy, n, C, labels_dev, class_off_dev, i0, p_mse, p_kld, p_acc, conf_dev);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
     return MPST_OK;

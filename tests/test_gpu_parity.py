@@ -336,3 +336,39 @@ def test_api_fitMPS_classify(pkg, oracle):
     assert abs(oracle._norm2_general(mps.mps) - 1.0) < 1e-10
     clf = pkg.MPSClassifier(d=3, chi_max=6, nsweeps=2).fit(X, y)
     assert clf.predict(Xt).shape == (120,)
+
+
+def test_device_metrics_match_host_reduction(ctx, oracle, pkg):
+    """f1: MSE_loss_acc_conf (summary.jl:60-114) reduced on the device (mpst_eval_metrics) == the oracle's per-sample
+    formulas, for a host data set with explicit labels and for the resident training set (labels = sorted class ranges),
+    in x mode and phi mode; more samples than one 65 536-sample batch is covered by the chunked N below."""
+    N, T, d = 70001, 6, 3                                  # two batches, ragged tail
+    Xs, phi, ys, counts, cores = _problem(oracle, N, T, d)
+    lab = np.repeat(np.arange(len(counts)), counts)
+    ctx.train_load_x(Xs, counts, d, 8)
+    ctx.set_cores(cores)
+    yh, am = ctx.overlaps(X_TxN=Xs)
+    onehot = np.eye(len(counts))[lab]
+    mse = 0.5 * np.sum((yh - onehot) ** 2)
+    kld = np.sum(-np.log(yh[np.arange(N), lab] ** 2))
+    pred = np.argmax(np.abs(yh), axis=1)
+    conf = np.zeros((2, 2), dtype=np.int64)
+    np.add.at(conf, (lab, pred), 1)
+    for kw in (dict(), dict(X_TxN=Xs, labels=lab)):
+        sums, cf, n = ctx.eval_metrics(**kw)
+        assert n == N and np.array_equal(cf, conf)
+        assert abs(sums[0] - mse) < 1e-11 * mse and abs(sums[1] - kld) < 1e-11 * abs(kld) and sums[2] == np.sum(pred == lab)
+    m_o, k_o, a_o = oracle.mse_loss_acc(cores, phi[:2000], lab[:2000])
+    sums, cf, n = ctx.eval_metrics(X_TxN=Xs[:, :2000], labels=lab[:2000])
+    assert abs(sums[0] / n - m_o) < 1e-11 * m_o and abs(sums[1] / n - k_o) < 1e-11 * abs(k_o) and abs(sums[2] / n - a_o) < 1e-15
+    # shuffled labels on a host set: the confusion matrix follows the labels, not the sort order
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(3000)
+    sums_p, cf_p, _ = ctx.eval_metrics(X_TxN=Xs[:, perm], labels=lab[perm])
+    sums_s, cf_s, _ = ctx.eval_metrics(X_TxN=Xs[:, np.sort(perm)], labels=lab[np.sort(perm)])
+    assert np.array_equal(cf_p, cf_s) and abs(sums_p[0] - sums_s[0]) < 1e-11 * sums_s[0]
+    ctx.train_load_phi(phi[:5000], np.array([np.sum(lab[:5000] == 0), np.sum(lab[:5000] == 1)]), 8)
+    ctx.set_cores(cores)
+    s1, c1, n1 = ctx.eval_metrics()
+    s2, c2, n2 = ctx.eval_metrics(phi_NTd=phi[:5000], labels=lab[:5000])
+    assert n1 == n2 == 5000 and np.array_equal(c1, c2) and np.allclose(s1, s2, rtol=1e-13)

@@ -165,3 +165,82 @@ def test_bench_reference_arm_contract():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["config"]["workload"].startswith("north_star_trendy_sine_N1M_T256_d16_chi64")
     assert line["scaling"] == "strong"
+
+
+def _julia_ccalls(src):
+    """[(symbol, return type, [argument types])] of every `ccall(sym(:name), Ret, (T1, T2, ...), ...)` in the shim."""
+    out = []
+    for m in re.finditer(r"ccall\(sym\(:(\w+)\),\s*(\w+),\s*\(", src):
+        i = m.end()
+        depth, j = 1, i
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[j], 0)
+            j += 1
+        body = src[i:j - 1]
+        args, cur, br = [], "", 0
+        for ch in body:
+            if ch == "{":
+                br += 1
+            elif ch == "}":
+                br -= 1
+            if ch == "," and br == 0:
+                args.append(cur.strip()); cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            args.append(cur.strip())
+        out.append((m.group(1), m.group(2), args))
+    return out
+
+
+def test_julia_shim_signatures_match_the_abi(pkg):
+    """julia/B200Backend.jl cannot run here (no Julia in the image); its ccall signatures and struct mirrors are checked
+    against the ctypes binding the GPU parity tests drive, and it must bind every symbol the header declares."""
+    import ctypes as C
+    from mpstime_jl_b200 import _lib
+    src = open(os.path.join(ROOT, "julia", "B200Backend.jl")).read()
+    jl2c = {
+        "Cint": C.c_int, "Int64": C.c_int64, "Float64": C.c_double, "Cstring": C.c_char_p, "Ptr{Cvoid}": C.c_void_p,
+        "Ref{Ptr{Cvoid}}": C.POINTER(C.c_void_p), "Ptr{Float64}": _lib.c_double_p, "Ref{Float64}": _lib.c_double_p,
+        "Ptr{Int64}": _lib.c_i64_p, "Ptr{Int32}": _lib.c_i32_p, "Ref{Int32}": _lib.c_i32_p, "Ptr{UInt8}": _lib.c_u8_p,
+        "Ref{TrainOpts}": C.POINTER(_lib.TrainOpts), "Ref{ImputeOpts}": C.POINTER(_lib.ImputeOpts),
+    }
+    calls = _julia_ccalls(src)
+    assert len(calls) >= len(pkg.SIGNATURES)
+    seen = set()
+    for name, ret, args in calls:
+        assert name in pkg.SIGNATURES, f"shim calls unknown symbol {name}"
+        res, argtypes = pkg.SIGNATURES[name]
+        assert jl2c[ret] is res, (name, ret, res)
+        assert len(args) == len(argtypes), (name, args, argtypes)
+        for k, (a, t) in enumerate(zip(args, argtypes)):
+            assert jl2c[a] is t, f"{name}: argument {k} is {a} in the shim, {t} in the binding"
+        seen.add(name)
+    assert seen == set(pkg.SIGNATURES), set(pkg.SIGNATURES) - seen
+    # struct mirrors: same field names, order and widths as the ctypes structures (= the C structs)
+    width = {"Int32": C.c_int32, "Float64": C.c_double}
+    for jl_name, cstruct in (("TrainOpts", _lib.TrainOpts), ("ImputeOpts", _lib.ImputeOpts)):
+        body = re.search(r"struct %s\b[^\n]*\n(.*?)\nend" % jl_name, src, re.S).group(1)
+        fields = re.findall(r"(\w+)::(\w+)", body)
+        assert [(n, width[t]) for n, t in fields] == [(n, t) for n, t in cstruct._fields_], jl_name
+    # the seams of SURVEY 8(b) are all defined
+    for fn in ("function fitMPS(W::MPS, training_states_meta::EncodedTimeSeriesSet", "function classify(mps::TrainedMPS",
+               "function get_predictions(imp::ImputationProblem", "function get_predictions_batch(", "function eval_loss(::ImputationLoss",
+               "function mlj_fit(m::MPSClassifier"):
+        assert fn in src, fn
+
+
+def test_options_refuse_what_the_device_path_does_not_implement(pkg):
+    """options that change the reference's results must raise, never be silently ignored; the encoding name
+    is normalised once (':Legendre', 'Legendre_No_Norm', ...)."""
+    for kw in (dict(projected_basis=True), dict(encode_classes_separately=True), dict(dtype=np.complex128),
+               dict(dtype=np.float32), dict(svd_alg="nonsense"), dict(use_legacy_ITensor=True), dict(loss_grad="Mixed")):
+        with pytest.raises(ValueError):
+            pkg.MPSOptions(**kw)._check()
+    for enc in (":Legendre", "Legendre_No_Norm", "legendre_norm", ":Uniform"):
+        o = pkg.MPSOptions(encoding=enc)
+        name = o._check()
+        assert pkg.preprocess.encoding_range(enc) == pkg.preprocess.encoding_range(name)
+        Xs, _ = pkg.transform_train_data(np.random.default_rng(0).standard_normal((7, 9)), o)
+        a, b = pkg.preprocess.encoding_range(name)
+        assert Xs.min() >= a - 1e-12 and Xs.max() <= b + 1e-12
