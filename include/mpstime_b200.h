@@ -47,7 +47,12 @@ enum {
     MPST_BASIS_STOUDENMIRE = 3,      /* bases.jl:13-20   (complex, d = 2) */
     MPST_BASIS_SAHAND = 4,           /* bases.jl:53-74   (complex, d even) */
     MPST_BASIS_UNIFORM = 5,          /* bases.jl:2-5 */
-    MPST_BASIS_PRECOMPUTED = 100     /* caller passes phi (data-driven / custom bases) */
+    MPST_BASIS_PRECOMPUTED = 100,    /* caller passes phi (custom bases) */
+    /* data-driven / time-dependent real bases: the host computes per-site coefficient tables once
+     * (bases.jl:294-397, splitbases.jl:13-110), the device evaluates them (mpst_set_encoding_table) */
+    MPST_BASIS_TABLE_LEGENDRE_PROJ = 101,   /* projected Legendre, bases.jl:95-108, 381-397           */
+    MPST_BASIS_TABLE_SAHAND_LEGENDRE = 102, /* Sahand-Legendre (time dependent or not), :111-129      */
+    MPST_BASIS_TABLE_SPLIT = 103            /* histogram / uniform split bases, splitbases.jl:113-163 */
 };
 
 enum { MPST_LOSS_KLD = 0, MPST_LOSS_MSE = 1 };     /* loss_functions.jl:322-432 / 561-619 */
@@ -86,6 +91,20 @@ int mpst_comm_init(mpst_ctx* ctx, const void* id128, int rank, int world);
  *      bases.jl:13-92).  x: n values already in the encoding range; out: d x n column-major
  *      (2 x d x n for complex bases). ---------------------------------------------------- */
 int mpst_encode(mpst_ctx* ctx, int basis_id, int d, const double* x, int64_t n, double* out);
+
+/* ---- coefficient tables of a data-driven / time-dependent encoding (replaces the `encoding_args` that
+ *      opts.encoding.init returns and encode_TS threads through, Encodings/encodings.jl:1-31).  n_sites = 1 for a
+ *      time-independent basis, else T.  Per site `ni` Int32 and `nd` Float64 values:
+ *        LEGENDRE_PROJ  : ip = d orders (0-based) followed by the inverse map order -> slot (-1 = unused) for orders
+ *                         0..L;  dp = { scale, L }
+ *        SAHAND_LEGENDRE: ip = { npts, has_data };  dp = { x_1, h, minx, scale, cVecs[d*d] (row n = basis function,
+ *                         column i = power of x), c[npts + 2] quadratic-B-spline coefficients of the KDE density }
+ *        SPLIT          : ip = { nbins, aux_dim, aux_basis_id };  dp = nbins + 1 bin edges
+ *      Call before mpst_train_load_x / mpst_model_init with basis_id = kind; the table stays until replaced. ---- */
+int mpst_set_encoding_table(mpst_ctx* ctx, int kind, int n_sites, int d, const int32_t* ip, int64_t ni,
+                            const double* dp, int64_t nd);
+/* K1 at one site of the context's current encoding (table or built-in): x: n values, out: d x n column-major. */
+int mpst_encode_site(mpst_ctx* ctx, int site, const double* x, int64_t n, double* out);
 
 /* ---- training set.  Replaces the PState / EncodedTimeSeriesSet / PCache containers
  *      (Structs/structs.jl:2-33) for the 4-arg fitMPS seam (RealRealHighDimension.jl:587).

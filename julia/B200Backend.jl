@@ -86,6 +86,59 @@ function encode(c::Ctx, basis_id::Integer, d::Integer, x::Vector{Float64})
     return cplx ? reinterpret(ComplexF64, out) : out
 end
 
+# ---- per-site coefficient tables of the data-driven / time-dependent real encodings (encode_table.cu) ----------------
+const TABLE_LEGENDRE_PROJ = 101; const TABLE_SAHAND_LEGENDRE = 102; const TABLE_SPLIT = 103
+
+set_encoding_table(c::Ctx, kind::Integer, n_sites::Integer, d::Integer, ip::Matrix{Int32}, dp::Matrix{Float64}) =   # columns = sites
+    chk(c, ccall(sym(:mpst_set_encoding_table), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int32}, Int64, Ptr{Float64}, Int64),
+                 c.h, kind, n_sites, d, ip, size(ip, 1), dp, size(dp, 1)))
+
+function encode_site(c::Ctx, site0::Integer, d::Integer, x::Vector{Float64})
+    out = Matrix{Float64}(undef, d, length(x))
+    chk(c, ccall(sym(:mpst_encode_site), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Ptr{Float64}), c.h, site0, x, length(x), out))
+    return out
+end
+
+# `encoding_args` (what opts.encoding.init returned, encodings.jl:112-120) -> device table.  fitMPS below does not need
+# this (it ships the reference's own PStates as phi); it lets classify / repeated fits skip the per-sample encode on the host.
+function encoding_table(opts::Options, enc_args::AbstractVector, T::Integer)
+    d = opts.d; name = opts.encoding.name
+    if startswith(name, "Projected Legendre")
+        ds = enc_args[1]                                                   # Vector (per site) of d orders
+        L = maximum(maximum.(ds))
+        ip = fill(Int32(-1), d + L + 1, T); dp = zeros(2, T)
+        for t in 1:T
+            ip[1:d, t] .= ds[t]
+            for (k, l) in enumerate(ds[t]); ip[d+l+1, t] = k - 1; end
+            dmax = maximum(ds[t])
+            dp[1, t] = endswith(name, "Norm") && dmax > 0 ? 1 / sqrt(sqrt((2dmax + 1) / 2) * dmax) : 1.0
+            dp[2, t] = maximum(ds[t])
+        end
+        return TABLE_LEGENDRE_PROJ, T, ip, dp
+    elseif startswith(name, "Sahand-Legendre")
+        td = opts.encoding.istimedependent
+        kdes, minxs, scales, cVecs = td ? enc_args : ([enc_args[1]], [enc_args[2]], [enc_args[3]], [enc_args[4]])
+        ns = length(cVecs); npts = 2048
+        ip = zeros(Int32, 2, ns); dp = zeros(4 + d * d + npts + 2, ns)
+        for t in 1:ns
+            ip[1, t] = npts; dp[2, t] = 1.0; dp[4, t] = 1.0
+            (isassigned(kdes, t) && !iszero(cVecs[t])) || continue
+            ik = Main.MPSTime.KernelDensity.InterpKDE(kdes[t])
+            ip[2, t] = 1
+            dp[1, t] = first(kdes[t].x); dp[2, t] = step(kdes[t].x); dp[3, t] = minxs[t]; dp[4, t] = scales[t]
+            dp[5:4+d*d, t] .= vec(permutedims(cVecs[t]))                   # row n = basis function, column i = power
+            dp[5+d*d:end, t] .= collect(ik.itp.itp.itp.coefs)              # padded quadratic-B-spline coefficients c[0..npts+1]
+        end
+        return TABLE_SAHAND_LEGENDRE, ns, ip, dp
+    else                                                                   # SplitBasis over a data-independent auxiliary basis
+        aux_enc_args, (bins, aux_dim, aux_enc) = enc_args
+        rows = eltype(bins) <: Number ? [bins] : bins
+        nb = length(rows[1]) - 1
+        ip = repeat(Int32[nb, aux_dim, BASIS_IDS[replace(aux_enc.name, "_No_Norm" => "")]], 1, length(rows))
+        return TABLE_SPLIT, length(rows), ip, reduce(hcat, rows)
+    end
+end
+
 # ---- model / training set ------------------------------------------------------------------------------------------
 model_init(c::Ctx, T, C, d, chi_max, basis_id) =
     chk(c, ccall(sym(:mpst_model_init), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint), c.h, T, C, d, chi_max, basis_id))

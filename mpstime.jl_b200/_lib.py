@@ -35,6 +35,8 @@ SIGNATURES = {
     "mpst_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mpst_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mpst_encode": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int64, c_double_p]),
+    "mpst_set_encoding_table": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_i32_p, C.c_int64, c_double_p, C.c_int64]),
+    "mpst_encode_site": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int64, c_double_p]),
     "mpst_train_load_x": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int, c_i64_p, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int64, c_i64_p]),
     "mpst_train_load_phi": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int, c_i64_p, C.c_int, C.c_int,

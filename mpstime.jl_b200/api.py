@@ -11,8 +11,9 @@ import numpy as np
 
 from . import dist as _dist
 from .core import Context, MPSTError, make_opts, BASIS_IDS
-from .preprocess import (encoding_range, generate_starting_mps, invert_test_transform, sort_by_class,
-                         transform_test_data, transform_train_data)
+from . import encodings_host as _eh
+from .preprocess import (_SL_NAMES, encoding_range, generate_starting_mps, invert_test_transform, sort_by_class,
+                         split_encoding_name, transform_test_data, transform_train_data)
 
 _ENC = {"legendre_no_norm": "legendre_no_norm", "legendre": "legendre_no_norm", "legendre_norm": "legendre_norm",
         "uniform": "uniform", "fourier": "fourier", "stoudenmire": "stoudenmire", "sahand": "sahand"}
@@ -49,12 +50,34 @@ class MPSOptions:
     use_legacy_ITensor: bool = False
     svd_alg: str = "divide_and_conquer"
 
+    def _table_spec(self):
+        """None for a built-in basis, else how to build the per-site coefficient table of a data-driven / time-dependent
+        encoding (model_encoding, Structs/options.jl:243-279): ("legendre_proj", norm) | ("sahand_legendre",
+        time_dependent) | ("split", method, aux)."""
+        enc = str(self.encoding).lower().lstrip(":")
+        if enc in _SL_NAMES:
+            return ("sahand_legendre", enc.startswith("sltd") or "time_dependent" in enc)
+        sp = split_encoding_name(enc)
+        if sp is not None:
+            if sp[1] not in _eh.AUX_IDS:
+                raise ValueError(f"split basis over {sp[1]!r}: the auxiliary basis must be a data-independent real basis "
+                                 "(Uniform, Legendre, Legendre_Norm); data-driven auxiliary bases are forbidden in the "
+                                 "reference too (splitbases.jl:33)")
+            if self.d % self.aux_basis_dim:
+                raise ValueError(f"The auxilliary basis dimension ({self.aux_basis_dim}) must evenly divide the total "
+                                 f"feature dimension ({self.d})")                          # splitbases.jl:4-6
+            return ("split", sp[0], sp[1])
+        if self.projected_basis and enc in ("legendre", "legendre_no_norm", "legendre_norm"):
+            return ("legendre_proj", enc == "legendre_norm")
+        return None
+
     def _check(self):
         enc = str(self.encoding).lower().lstrip(":")
-        if enc not in _ENC:
-            raise ValueError(f"encoding {self.encoding!r}: only the data-independent bases run on the device "
-                             "(Legendre, Legendre_No_Norm, Legendre_Norm, Uniform for training; "
-                             "Fourier/Stoudenmire/Sahand for mpst_encode)")
+        table = self._table_spec()
+        if enc not in _ENC and table is None:
+            raise ValueError(f"encoding {self.encoding!r}: unknown to the B200 backend (built-in: Legendre, Legendre_No_Norm, "
+                             "Legendre_Norm, Uniform; from per-site tables: projected Legendre, SL / SLTD, hist_split_* / "
+                             "unif_split_*; Fourier / Stoudenmire / Sahand only through mpst_encode)")
         if enc in ("fourier", "stoudenmire", "sahand"):
             # loss_functions.jl:343 keeps yhat in a Ref{Float64}: the array path is real-only
             raise ValueError("complex encodings cannot be trained on the array path (reference: InexactError)")
@@ -68,18 +91,19 @@ class MPSOptions:
             raise ValueError("use_legacy_ITensor=true selects the reference's own ITensor trainer; not this backend")
         # options that change the reference's results and that the device path does not implement are refused,
         # never silently ignored
-        if self.projected_basis:
-            raise ValueError("projected_basis=true is not implemented by the B200 backend")
+        if self.projected_basis and table is None:
+            raise ValueError("projected_basis=true: only the projected Legendre bases are real-valued and trainable "
+                             "(projected Fourier is complex, loss_functions.jl:343)")
         if self.encode_classes_separately:
-            raise ValueError("encode_classes_separately=true only affects data-driven bases (Encodings/encodings.jl:112-131), "
-                             "which the B200 backend takes as precomputed phi (mpst_train_load_phi)")
+            raise ValueError("encode_classes_separately=true (one table per class, Encodings/encodings.jl:57-77) is not "
+                             "implemented by the B200 backend; pass precomputed phi (mpst_train_load_phi) instead")
         if np.dtype(self.dtype) != np.dtype(np.float64):
             raise ValueError(f"dtype {self.dtype!r}: the array training path is Float64-only (loss_functions.jl:343)")
         if str(self.svd_alg).lstrip(":") not in ("divide_and_conquer", "qr_iteration", "recursive"):
             raise ValueError(f"unknown svd_alg {self.svd_alg!r}")
         # svd_alg picks the LAPACK driver in the reference; every choice yields the same truncated factors up to
         # rounding, and the device SVD (K5) replaces all of them
-        return _ENC[enc]
+        return _ENC[enc] if table is None else "table_" + table[0]
 
 
 @dataclass
@@ -98,6 +122,7 @@ class TrainedMPS:
     opts: MPSOptions
     train_data: EncodedTimeSeriesSet
     classes: np.ndarray = None
+    enc_table: tuple = None         # (kind, n_sites, ip, dp) of a data-driven encoding: the reference's `encoding_args`
 
 
 _CTX = {}
@@ -180,6 +205,11 @@ def fitMPS(X_train, y_train=None, X_test=None, y_test=None, opts: Optional[MPSOp
         X_local, counts_local, _ = _dist.shard_samples(Xs_sorted, counts, rank, world)
     else:
         X_local, counts_local = Xs_sorted, counts
+    # opts.encoding.init on the whole (unsharded) normalised training set (Encodings/encodings.jl:112-120): host work,
+    # once per fit; the device evaluates the resulting per-site tables
+    enc_table = build_encoding_table(opts, Xs_sorted)
+    if enc_table is not None:
+        ctx.set_encoding_table(enc_table[0], enc_table[1], opts.d, enc_table[2], enc_table[3])
     ctx.train_load_x(X_local, counts_local, opts.d, opts.chi_max, basis=enc, n_global=N, counts_global=counts)
     cores0 = W if W is not None else generate_starting_mps(opts.chi_init, T, opts.d, C, seed=opts.init_rng)
     ctx.set_cores(cores0)
@@ -220,8 +250,21 @@ def fitMPS(X_train, y_train=None, X_test=None, y_test=None, opts: Optional[MPSOp
     cores = _normalize(ctx.get_cores())                                     # :852
     ctx.set_cores(cores)
     log(float("nan"))                                                       # :854-885
-    mps = TrainedMPS(cores, replace(opts), train_states, classes)
+    mps = TrainedMPS(cores, replace(opts), train_states, classes, enc_table)
     return mps, info, test_states
+
+
+def build_encoding_table(opts, Xs_sorted_TxN):
+    """`encoding_args = opts.encoding.init(X_norm, y; opts)` (encodings.jl:112-120) as a device table, or None."""
+    spec = opts._table_spec()
+    if spec is None:
+        return None
+    rng_ = encoding_range(opts.encoding)
+    if spec[0] == "legendre_proj":
+        return _eh.project_legendre(Xs_sorted_TxN, opts.d, norm=spec[1], enc_range=rng_)[0]
+    if spec[0] == "sahand_legendre":
+        return _eh.init_sahand_legendre(Xs_sorted_TxN, opts.d, time_dependent=spec[1], enc_range=rng_)
+    return _eh.split_table(Xs_sorted_TxN, opts.d, opts.aux_basis_dim, aux=spec[2], method=spec[1], enc_range=rng_)
 
 
 def _normalize(cores):
@@ -241,6 +284,8 @@ def _load_model(ctx, mps: TrainedMPS):
     T = len(mps.mps)
     C = [A for A in mps.mps if A.ndim == 4][0].shape[3]
     chi = max(max(A.shape[0], A.shape[2]) for A in mps.mps)
+    if mps.enc_table is not None:
+        ctx.set_encoding_table(mps.enc_table[0], mps.enc_table[1], mps.opts.d, mps.enc_table[2], mps.enc_table[3])
     ctx.model_init(T, C, mps.opts.d, max(chi, 1), basis=enc)
     ctx.set_cores(mps.mps)
     return enc, T, C

@@ -10,8 +10,11 @@ from ._lib import ImputeOpts, TrainOpts, c_double_p, c_i32_p, c_i64_p, c_u8_p
 BASIS_IDS = {
     "legendre_no_norm": 0, "legendre": 0, "legendre_norm": 1, "fourier": 2, "stoudenmire": 3,
     "sahand": 4, "uniform": 5, "precomputed": 100,
+    # data-driven / time-dependent real bases: evaluated from per-site coefficient tables (set_encoding_table)
+    "table_legendre_proj": 101, "table_sahand_legendre": 102, "table_split": 103,
 }
-BASIS_RANGE = {0: (-1.0, 1.0), 1: (-1.0, 1.0), 2: (-1.0, 1.0), 3: (0.0, 1.0), 4: (0.0, 1.0), 5: (0.0, 1.0)}
+BASIS_RANGE = {0: (-1.0, 1.0), 1: (-1.0, 1.0), 2: (-1.0, 1.0), 3: (0.0, 1.0), 4: (0.0, 1.0), 5: (0.0, 1.0),
+               101: (-1.0, 1.0), 102: (-1.0, 1.0)}
 LOSS_IDS = {"KLD": 0, "MSE": 1}
 OPT_IDS = {"TSGO": 0, "GD": 1}
 METHOD_IDS = {"median": 0, "mean": 1, "mode": 2, "ITS": 3}
@@ -99,9 +102,24 @@ class Context:
             out = out.view(np.complex128)
         return out.reshape(x.shape + (d,))
 
+    def set_encoding_table(self, kind, n_sites, d, ip, dp):
+        """Per-site coefficient tables of a data-driven / time-dependent encoding (encodings_host.py builds them)."""
+        ip = np.ascontiguousarray(ip, dtype=np.int32).reshape(n_sites, -1)
+        dp = np.ascontiguousarray(dp, dtype=np.float64).reshape(n_sites, -1)
+        self._chk(self.lib.mpst_set_encoding_table(self.h, int(kind), int(n_sites), int(d), ip.ctypes.data_as(c_i32_p),
+                                                   ip.shape[1], _dp(dp), dp.shape[1]))
+
+    def encode_site(self, site, x):
+        """K1 at one site of the context's current encoding -> (n, d)."""
+        x = _f64(x).reshape(-1)
+        out = np.empty((x.size, self.d), dtype=np.float64)
+        self._chk(self.lib.mpst_encode_site(self.h, int(site), _dp(x), x.size, _dp(out)))
+        return out
+
     # ---- training set -----------------------------------------------------------------------
     def model_init(self, T, C_, d, chi_max, basis="legendre_no_norm"):
-        self._chk(self.lib.mpst_model_init(self.h, int(T), int(C_), int(d), int(chi_max), BASIS_IDS[basis.lower()]))
+        self._chk(self.lib.mpst_model_init(self.h, int(T), int(C_), int(d), int(chi_max),
+                                           basis if isinstance(basis, int) else BASIS_IDS[basis.lower()]))
         self.T, self.C, self.d = int(T), int(C_), int(d)
 
     def train_load_x(self, X_TxN, class_counts, d, chi_max, basis="legendre_no_norm", n_global=0,
@@ -113,7 +131,7 @@ class Context:
         cc = np.ascontiguousarray(class_counts, dtype=np.int64)
         cg = np.ascontiguousarray(counts_global if counts_global is not None else class_counts, dtype=np.int64)
         self._chk(self.lib.mpst_train_load_x(self.h, _dp(Xh), N, T, cc.ctypes.data_as(c_i64_p), len(cc),
-                                             BASIS_IDS[basis.lower()], int(d), int(chi_max), int(n_global or N),
+                                             basis if isinstance(basis, int) else BASIS_IDS[basis.lower()], int(d), int(chi_max), int(n_global or N),
                                              cg.ctypes.data_as(c_i64_p)))
         self.T, self.C, self.d = T, len(cc), int(d)
 

@@ -320,6 +320,8 @@ int mpst_destroy(mpst_ctx* c) {
     auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(c->B); fr(c->G); fr(c->Z); fr(c->part); fr(c->red); fr(c->scal); fr(c->S); fr(c->gpart); fr(c->wbuf);
     fr(c->colnorm); fr(c->tmp); fr(c->meta); fr(c->sub); fr(c->gws);
+    if (c->enc.ip) cudaFree(c->enc.ip);
+    if (c->enc.dp) cudaFree(c->enc.dp);
     for (int i = 0; i < 16; i++) if (c->imp_ptr[i]) cudaFree(c->imp_ptr[i]);
     if (c->hmeta) cudaFreeHost(c->hmeta);
     if (c->perm) cudaFree(c->perm);
@@ -455,10 +457,15 @@ int mpst_model_init(mpst_ctx* c, int T, int C, int d, int chi_max, int basis_id)
 int mpst_train_load_x(mpst_ctx* c, const double* X, int64_t N, int T, const int64_t* class_counts, int C,
                       int basis_id, int d, int chi_max, int64_t n_global, const int64_t* counts_global) {
     if (!c || !X || !class_counts) return MPST_E_INVALID;
-    if (basis_id != MPST_BASIS_LEGENDRE_NO_NORM && basis_id != MPST_BASIS_LEGENDRE_NORM && basis_id != MPST_BASIS_UNIFORM) {
+    const bool table = basis_id >= MPST_BASIS_TABLE_LEGENDRE_PROJ && basis_id <= MPST_BASIS_TABLE_SPLIT;
+    if (basis_id != MPST_BASIS_LEGENDRE_NO_NORM && basis_id != MPST_BASIS_LEGENDRE_NORM && basis_id != MPST_BASIS_UNIFORM && !table) {
         // loss_functions.jl keeps yhat in a Ref{Float64}: the array training path is real-only
         c->err = "train_load_x: the training path is real-valued; complex bases are not supported";
         return MPST_E_UNSUPPORTED;
+    }
+    if (table && (c->enc.kind != basis_id || c->enc.d != d || (c->enc.nsites != 1 && c->enc.nsites != T))) {
+        c->err = "train_load_x: set the coefficient table of this encoding first (mpst_set_encoding_table: same kind, d, 1 or T sites)";
+        return MPST_E_INVALID;
     }
     TRY(train_common(c, N, T, class_counts, C, d, chi_max, n_global, counts_global));
     c->basis = basis_id;
@@ -491,6 +498,57 @@ int mpst_train_load_phi(mpst_ctx* c, const double* phi, int64_t N, int T, const 
     for (int j = 0; j < T; j++)
         CUDA_TRY(c, cudaMemcpy2DAsync(c->PHI + (size_t)j * c->Npad * d, sizeof(double) * d, phi + (size_t)j * d,
                                       sizeof(double) * d * T, sizeof(double) * d, N, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MPST_OK;
+}
+
+int mpst_set_encoding_table(mpst_ctx* c, int kind, int n_sites, int d, const int32_t* ip, int64_t ni, const double* dp,
+                            int64_t nd) {
+    if (!c || !ip || !dp || n_sites < 1 || d < 1 || d > MPST_MAX_D || ni < 1 || nd < 1) return MPST_E_INVALID;
+    if (kind < MPST_BASIS_TABLE_LEGENDRE_PROJ || kind > MPST_BASIS_TABLE_SPLIT) { c->err = "set_encoding_table: unknown kind"; return MPST_E_INVALID; }
+    // validate what the kernels index with
+    for (int s = 0; s < n_sites; s++) {
+        const int32_t* p = ip + (size_t)s * ni;
+        const double* q = dp + (size_t)s * nd;
+        bool ok = true;
+        if (kind == MPST_BASIS_TABLE_LEGENDRE_PROJ) {
+            const int L = (int)q[1];
+            ok = nd >= 2 && L >= 0 && ni >= d + L + 1;
+            for (int l = 0; ok && l <= L; l++) ok = p[d + l] >= -1 && p[d + l] < d;
+        } else if (kind == MPST_BASIS_TABLE_SAHAND_LEGENDRE) {
+            ok = ni >= 2 && p[0] >= 2 && nd >= 4 + (int64_t)d * d + p[0] + 2 && (!p[1] || (q[1] > 0.0 && q[3] != 0.0));
+        } else {
+            ok = ni >= 3 && p[0] >= 1 && p[1] >= 1 && p[0] * p[1] == d && nd >= p[0] + 1 && p[1] <= MPST_MAX_D &&
+                 (p[2] == MPST_BASIS_LEGENDRE_NO_NORM || p[2] == MPST_BASIS_LEGENDRE_NORM || p[2] == MPST_BASIS_UNIFORM);
+            for (int i = 0; ok && i < p[0]; i++) ok = q[i + 1] >= q[i];
+        }
+        if (!ok) { c->err = "set_encoding_table: inconsistent table at site " + std::to_string(s); return MPST_E_INVALID; }
+    }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->enc.ip) cudaFree(c->enc.ip);
+    if (c->enc.dp) cudaFree(c->enc.dp);
+    c->enc = EncTable();
+    CUDA_TRY(c, cudaMalloc(&c->enc.ip, sizeof(int) * (size_t)n_sites * ni));
+    CUDA_TRY(c, cudaMalloc(&c->enc.dp, sizeof(double) * (size_t)n_sites * nd));
+    CUDA_TRY(c, cudaMemcpy(c->enc.ip, ip, sizeof(int) * (size_t)n_sites * ni, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->enc.dp, dp, sizeof(double) * (size_t)n_sites * nd, cudaMemcpyHostToDevice));
+    c->enc.kind = kind; c->enc.nsites = n_sites; c->enc.d = d; c->enc.istride = ni; c->enc.dstride = nd;
+    return MPST_OK;
+}
+
+int mpst_encode_site(mpst_ctx* c, int site, const double* x, int64_t n, double* out) {
+    if (!c || !x || !out || n < 0 || c->d < 1) return MPST_E_INVALID;
+    if (n == 0) return MPST_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int d = c->d;
+    TRY(ensure_buf(c, &c->tmp, &c->tmpcap, (size_t)n * (d + 1)));
+    CUDA_TRY(c, cudaMemcpyAsync(c->tmp, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    {
+        ProfScope ps(c, MPST_T_ENCODE);
+        TRY(launch_encode_site(c, site, c->tmp, n, c->tmp + n, d));
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->tmp + n, (size_t)n * d * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return MPST_OK;
 }
@@ -545,7 +603,7 @@ int mpst_get_core(mpst_ctx* c, int site, double* out) {
 static int site_phi(mpst_ctx* c, int site, double* dst, const double** out) {
     if (c->have_phi) { *out = c->PHI + (size_t)site * c->Npad * c->d; return MPST_OK; }
     ProfScope ps(c, MPST_T_ENCODE);
-    TRY(launch_encode(c, c->basis, c->d, c->X + (size_t)site * c->Npad, c->N, dst, c->d));
+    TRY(launch_encode_site(c, site, c->X + (size_t)site * c->Npad, c->N, dst, c->d));
     *out = dst;
     return MPST_OK;
 }
@@ -981,7 +1039,7 @@ static int overlaps_impl(mpst_ctx* c, const double* X_or_phi, int64_t n, double*
                     *out = resident ? c->PHI + ((size_t)j * c->Npad + i0) * d : xin + (size_t)j * BP * d;
                     return MPST_OK;
                 }
-                TRY(launch_encode(c, c->basis, d, resident ? c->X + (size_t)j * c->Npad + i0 : xin + (size_t)j * BP, nn, ph, d));
+                TRY(launch_encode_site(c, j, resident ? c->X + (size_t)j * c->Npad + i0 : xin + (size_t)j * BP, nn, ph, d));
                 *out = ph;
                 return MPST_OK;
             };

@@ -69,6 +69,13 @@ enum {
     L_COUNT
 };
 
+struct EncTable {        // per-site coefficient tables of a data-driven / time-dependent encoding (encode_table.cu)
+    int kind = 0, nsites = 0, d = 0;
+    int64_t istride = 0, dstride = 0;
+    int* ip = nullptr;      // device [nsites][istride]
+    double* dp = nullptr;   // device [nsites][dstride]
+};
+
 struct SegTable {       // cached stream-K schedule of one (kernel variant, shape, class ranges) combination
     std::vector<int64_t> key;
     GradSeg* segs = nullptr;     // device
@@ -111,6 +118,7 @@ struct mpst_ctx {
     double* hscal = nullptr;    // pinned host mirror
     std::vector<SegTable> segtabs;   // stream-K schedules, built once per shape (no per-bond host work / sync)
     uint64_t seg_clock = 0;
+    EncTable enc;
     int flag[F_COUNT] = {0};
     int last[L_COUNT] = {0};
     // cursor of mpst_sweep_bonds: next bond of the (backward, forward) cycle, -1 = not started
@@ -189,6 +197,7 @@ static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * 
 
 // ---- kernels (defined in the .cu files) -------------------------------------------------------
 int launch_encode(mpst_ctx* c, int basis, int d, const double* x, int64_t n, double* out, int64_t ldo);
+int launch_encode_site(mpst_ctx* c, int site, const double* x, int64_t n, double* out, int64_t ldo);
 int launch_permute_core(mpst_ctx* c, const double* src, double* dst, int d, int chi_l, int chi_r,
                         int C, long ss, long sa, long sb, long sc, long ds, long da, long db, long dc);
 int launch_krao_gemm_rows(mpst_ctx* c, const double* x, const double* E, const double* W, double* out,

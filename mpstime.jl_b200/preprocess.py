@@ -6,9 +6,30 @@ import numpy as np
 from .core import BASIS_IDS, BASIS_RANGE
 
 
+_SL_NAMES = ("sl", "sahand_legendre", "sahand_legendre_time_independent", "sahand-legendre_time_independent",
+             "sltd", "sahand_legendre_time_dependent", "sahand-_legendre_time_dependent")
+
+
+def split_encoding_name(basis):
+    """("hist" | "unif", auxiliary basis name) of a split-basis symbol (options.jl:261-272), else None."""
+    s = str(basis).lower().lstrip(":")
+    for pre, kind in (("hist_split_", "hist"), ("hist._split_", "hist"), ("histogram_split_", "hist"),
+                      ("unif_split_", "unif"), ("unif._split_", "unif"), ("uniform_split_", "unif")):
+        if s.startswith(pre):
+            return kind, s[len(pre):]
+    return None
+
+
 def encoding_range(basis):
-    """Domain of a basis; accepts the reference's spellings ("Legendre_No_Norm", ":legendre", Symbol-style)."""
-    return BASIS_RANGE[BASIS_IDS[str(basis).lower().lstrip(":")]]
+    """Domain of a basis; accepts the reference's spellings ("Legendre_No_Norm", ":legendre", ":SLTD",
+    ":hist_split_uniform", ...) -- model_encoding, Structs/options.jl:243-279."""
+    s = str(basis).lower().lstrip(":")
+    if s in _SL_NAMES:
+        return (-1.0, 1.0)
+    sp = split_encoding_name(s)
+    if sp is not None:
+        return encoding_range(sp[1])                          # a split basis inherits the range of its auxiliary basis
+    return BASIS_RANGE[BASIS_IDS[s]]
 
 
 class Norms:

@@ -228,6 +228,73 @@ def encode(x, d, basis="legendre_no_norm"):
     raise ValueError(basis)
 
 
+# --------------------------------------------------------------------------------------
+# data-driven / time-dependent encodings GIVEN their initialised arguments (bases.jl:95-129,
+# splitbases.jl:96-163).  The initialisers themselves (KDE, series projections, histogram bins) are
+# host-side in the reference and in the product; the oracle restates what is evaluated per point.
+# --------------------------------------------------------------------------------------
+
+def projected_legendre_encode(x, orders, norm=False):
+    """legendre_encode(x, nds, ds; norm) (bases.jl:95-108): the normalised Legendre polynomials of the given
+    orders; with norm the vector is divided by sqrt(Pl(1, dmax) * dmax), dmax = maximum(ds)."""
+    orders = np.asarray(orders, dtype=np.int64)
+    full = legendre_encode(np.asarray(x, dtype=np.float64), int(orders.max()) + 1)
+    out = full[..., orders]
+    if norm:
+        dmax = int(orders.max())
+        out = out / np.sqrt(np.sqrt((2 * dmax + 1) / 2.0) * dmax)
+    return out
+
+
+def interp_kde_pdf(x, kde_x, coeffs):
+    """pdf(kde, x) (KernelDensity.InterpKDE, un-vendored): quadratic B-spline through the tabulated density
+    (Interpolations BSpline(Quadratic(Line(OnGrid()))), padded coefficients), zero outside the grid."""
+    x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    out = np.zeros_like(x)
+    n = len(kde_x)
+    h = kde_x[1] - kde_x[0]
+    for k, xv in enumerate(x):
+        t = (xv - kde_x[0]) / h + 1.0
+        if t < 1.0 or t > n:
+            continue
+        i = int(np.rint(t))
+        dx = t - i
+        out[k] = coeffs[i - 1] * (dx - 0.5) ** 2 / 2 + coeffs[i] * (0.75 - dx ** 2) + coeffs[i + 1] * (dx + 0.5) ** 2 / 2
+    return out
+
+
+def sahand_legendre_encode(x, d, kde_x, coeffs, minx, scale, cVecs):
+    """sahand_legendre_encode (bases.jl:111-117): f_n(x) = (sum_i cVecs[n,i] x^(i-1)) * f0(x) / scale,
+    f0 = max(sqrt(max(pdf(kde, x), 0)), minx)."""
+    x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    f0 = np.maximum(np.sqrt(np.maximum(interp_kde_pdf(x, kde_x, coeffs), 0.0)), minx)
+    powers = x[:, None] ** np.arange(d)[None, :]
+    return (powers @ np.asarray(cVecs).T) * f0[:, None] / scale
+
+
+def split_encode(x, bins, aux_dim, aux_basis="uniform"):
+    """project_onto_bins (splitbases.jl:113-140) with rect (:96-109): the auxiliary basis, evaluated at the position
+    inside the bin stretched to the whole range, in the slot of the bin containing x; a point exactly on an inner
+    edge gets weight 1/2 in both neighbours."""
+    x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    bins = np.asarray(bins, dtype=np.float64)
+    nb = len(bins) - 1
+    a, b = bins[0], bins[-1]
+    scale = b - a
+    out = np.zeros((len(x), nb * aux_dim))
+    for k, xv in enumerate(x):
+        for i in range(nb):
+            dxb = bins[i + 1] - bins[i]
+            xprop = scale * (xv - bins[i]) / dxb
+            r = xprop / scale - 0.5
+            lb = 1.0 if i == 0 else 0.5
+            rb = 1.0 if i == nb - 1 else 0.5
+            sel = lb if r == -0.5 else rb if r == 0.5 else 1.0 if -0.5 <= r <= 0.5 else 0.0
+            if sel != 0.0:
+                out[k, i * aux_dim:(i + 1) * aux_dim] = sel * encode(np.array([a + xprop]), aux_dim, aux_basis)[0]
+    return out
+
+
 def encode_dataset(X_scaled, y, d, basis="legendre_no_norm"):
     """encode_dataset -> encode_safe_dataset (encodings.jl:33-46, 79-156): stable sort by class
     (`sortperm`), encode every (sample, site).  X_scaled is T x N (series are columns).

@@ -233,7 +233,9 @@ def test_julia_shim_signatures_match_the_abi(pkg):
 def test_options_refuse_what_the_device_path_does_not_implement(pkg):
     """options that change the reference's results must raise, never be silently ignored; the encoding name
     is normalised once (':Legendre', 'Legendre_No_Norm', ...)."""
-    for kw in (dict(projected_basis=True), dict(encode_classes_separately=True), dict(dtype=np.complex128),
+    for kw in (dict(projected_basis=True, encoding="Fourier"), dict(projected_basis=True, encoding="Uniform"),
+               dict(encode_classes_separately=True), dict(dtype=np.complex128), dict(encoding="hist_split_fourier", d=4),
+               dict(encoding="hist_split_uniform", d=5, aux_basis_dim=2),
                dict(dtype=np.float32), dict(svd_alg="nonsense"), dict(use_legacy_ITensor=True), dict(loss_grad="Mixed")):
         with pytest.raises(ValueError):
             pkg.MPSOptions(**kw)._check()
