@@ -182,7 +182,7 @@ def fitMPS(X_train, y_train=None, X_test=None, y_test=None, opts: Optional[MPSOp
     has_test = X_test is not None and np.size(X_test) > 0
     Xs_train, norms = transform_train_data(X_train.T, opts)                # :445
     Xs_sorted, Xo_sorted, ys, _, classes, counts = sort_by_class(Xs_train, X_train, y_train)
-    a, b = encoding_range(enc)
+    a, b = encoding_range(opts.encoding)
     if not np.all((a <= Xs_sorted) & (Xs_sorted <= b)):
         raise ValueError(f"Data must be rescaled between {a} and {b} before a {opts.encoding} encoding.")
     C = len(classes)
@@ -339,7 +339,7 @@ def init_imputation_problem(mps: TrainedMPS, X_test, y_test=None, dx=1e-4, guess
     y_test = np.zeros(X_test.shape[0], dtype=np.int64) if y_test is None else np.asarray(y_test)
     X_train = mps.train_data.original_data
     y_train = mps.train_data.labels
-    rng_ = guess_range or encoding_range(enc)
+    rng_ = guess_range or encoding_range(opts.encoding)
     xvals = make_grid(rng_, dx)
     _, norms = transform_train_data(X_train, opts)          # hoisted out of get_predictions (:287)
     class_map = {c: i for i, c in enumerate(sorted(np.unique(y_train)))}
