@@ -295,18 +295,24 @@ int launch_bond_grad_kr(mpst_ctx* c, const double* xl, const double* xr, const d
     if ((chi_l & 1) || (chi_r & 1) || chi_l < 8 || chi_r < 8) return MPST_OK;       // 16-byte rows for the bulk copies
     auto ring = [&](int kc, int sr) { return 128 + sizeof(double) * (size_t)sr * (kc * (chi_l + chi_r + 2 * d) + kc); };
     const int forced = c->flag[F_GRAD_KC];
-    const bool big = ring(64, 3) <= 227 * 1024 && forced != 32;
-    if (!big && ring(32, 4) > 227 * 1024) return MPST_OK;
-    const size_t smem = big ? ring(64, 3) : ring(32, 4);
+    // stage size by what fits: 64 x 3 (config B), 32 x 4 (d = 16, chi = 64), 16 x 4 (chi = 128)
+    const int kc = (ring(64, 3) <= 227 * 1024 && forced != 32 && forced != 16) ? 64
+                 : (ring(32, 4) <= 227 * 1024 && forced != 16) ? 32 : 16;
+    const size_t smem = kc == 64 ? ring(64, 3) : ring(kc, 4);
+    if (smem > 227 * 1024) return MPST_OK;
+#define KR_ARGS c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem
     if (d % 6 == 0) {
         *handled = true;
-        if (big) return launch_kr<1, 6, 1, 6, 8, 64, 3>(c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem);
-        return launch_kr<1, 6, 1, 6, 8, 32, 4>(c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem);
+        if (kc == 64) return launch_kr<1, 6, 1, 6, 8, 64, 3>(KR_ARGS);
+        if (kc == 32) return launch_kr<1, 6, 1, 6, 8, 32, 4>(KR_ARGS);
+        return launch_kr<1, 6, 1, 6, 8, 16, 4>(KR_ARGS);
     }
     if (d % 4 == 0) {
         *handled = true;
-        if (big) return launch_kr<2, 4, 1, 4, 8, 64, 3>(c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem);
-        return launch_kr<2, 4, 1, 4, 8, 32, 4>(c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem);
+        if (kc == 64) return launch_kr<2, 4, 1, 4, 8, 64, 3>(KR_ARGS);
+        if (kc == 32) return launch_kr<2, 4, 1, 4, 8, 32, 4>(KR_ARGS);
+        return launch_kr<2, 4, 1, 4, 8, 16, 4>(KR_ARGS);
     }
+#undef KR_ARGS
     return MPST_OK;
 }
