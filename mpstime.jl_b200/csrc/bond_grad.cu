@@ -287,6 +287,15 @@ int launch_bond_grad(mpst_ctx* c, const double* xl, const double* xr, const doub
         }
         hslot[ntiles] = (int)hsegs.size();
         while (cta < ncta) { cta++; hcta[cta] = (int)hsegs.size(); }
+        // L2 sharing: a CTA's contiguous range usually ends one pass over the samples and begins the next one at chunk 0.
+        // Walking its segments in ascending chunk order makes every CTA start at the first samples and move through the
+        // data set together (two fronts a fixed distance apart), so the raw rows one CTA pulls from HBM are L2 hits for
+        // the others -- without it each of the ~64 output groups streamed the whole data set from DRAM on its own
+        // (ncu: 54x the algorithmic bytes at the north-star shape).  Slots keep their table position, so the fixed-order
+        // segment reduction is unchanged.
+        for (int i = 0; i < ncta; i++)
+            std::stable_sort(hsegs.begin() + hcta[i], hsegs.begin() + hcta[i + 1],
+                             [](const GradSeg& a, const GradSeg& b) { return a.chunk_begin < b.chunk_begin; });
         TRY(segtable_add(c, key, hsegs, hcta, hslot, &tab));
     }
     const int nseg = tab->nseg;

@@ -234,7 +234,7 @@ int launch_kr(mpst_ctx* c, const double* xl, const double* xr, const double* L, 
         return MPST_OK;
     }
     // The schedule depends only on (kernel variant, group count, class chunk ranges): built once, kept on the device
-    std::vector<int64_t> key = {1, MA, S, NB, T, NW, KC, ncta, geo.ngroups, ncls};
+    std::vector<int64_t> key = {1, MA, S, NB, T, NW, KC, SR, ncta, geo.ngroups, ncls};
     for (int k = 0; k < ncls; k++) { key.push_back(cb[k]); key.push_back(ce[k]); }
     SegTable* tab = segtable_find(c, key);
     if (!tab) {
@@ -263,6 +263,15 @@ int launch_kr(mpst_ctx* c, const double* xl, const double* xr, const double* L, 
         }
         hslot[ngrp_total] = (int)hsegs.size();
         while (cta < ncta) { cta++; hcta[cta] = (int)hsegs.size(); }
+        // L2 sharing: a CTA's contiguous range usually ends one pass over the samples and begins the next one at chunk 0.
+        // Walking its segments in ascending chunk order makes every CTA start at the first samples and move through the
+        // data set together (two fronts a fixed distance apart), so the raw rows one CTA pulls from HBM are L2 hits for
+        // the others -- without it each of the ~64 output groups streamed the whole data set from DRAM on its own
+        // (ncu: 54x the algorithmic bytes at the north-star shape).  Slots keep their table position, so the fixed-order
+        // segment reduction is unchanged.
+        for (int i = 0; i < ncta; i++)
+            std::stable_sort(hsegs.begin() + hcta[i], hsegs.begin() + hcta[i + 1],
+                             [](const GradSeg& a, const GradSeg& b) { return a.chunk_begin < b.chunk_begin; });
         TRY(segtable_add(c, key, hsegs, hcta, hslot, &tab));
     }
     const int nseg = tab->nseg;
@@ -270,7 +279,7 @@ int launch_kr(mpst_ctx* c, const double* xl, const double* xr, const double* L, 
     TRY(ensure_buf(c, &c->part, &c->partcap, (size_t)nseg * NW * RU * CU));
     c->last[L_GRAD_KERNEL] = 1;
     c->last[L_GRAD_KR_LAUNCHES]++;
-    c->last[L_GRAD_VARIANT] = MA * 1000 + S * 100 + KC;
+    c->last[L_GRAD_VARIANT] = MA * 10000 + S * 1000 + KC * 10 + SR;
     auto kern = bond_grad_kr_kernel<MA, S, NB, T, NW, KC, SR>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(c, MPST_T_GRADK);
@@ -295,24 +304,30 @@ int launch_bond_grad_kr(mpst_ctx* c, const double* xl, const double* xr, const d
     if ((chi_l & 1) || (chi_r & 1) || chi_l < 8 || chi_r < 8) return MPST_OK;       // 16-byte rows for the bulk copies
     auto ring = [&](int kc, int sr) { return 128 + sizeof(double) * (size_t)sr * (kc * (chi_l + chi_r + 2 * d) + kc); };
     const int forced = c->flag[F_GRAD_KC];
-    // stage size by what fits: 64 x 3 (config B), 32 x 4 (d = 16, chi = 64), 16 x 4 (chi = 128)
-    const int kc = (ring(64, 3) <= 227 * 1024 && forced != 32 && forced != 16) ? 64
-                 : (ring(32, 4) <= 227 * 1024 && forced != 16) ? 32 : 16;
-    const size_t smem = kc == 64 ? ring(64, 3) : ring(kc, 4);
-    if (smem > 227 * 1024) return MPST_OK;
+    // stage size x ring depth by what fits: 64 x 4 or 64 x 3 (config B), 32 x 4 (d = 16, chi = 64), 16 x 4 (chi = 128);
+    // GRAD_KC = kc * 10 + sr forces a variant (A/B measurements)
+    const int lim = 227 * 1024;
+    int kc, sr;
+    if (forced >= 100) { kc = forced / 10; sr = forced % 10; }
+    else if (ring(64, 4) <= (size_t)lim && c->flag[F_GRAD_KC] == 0 && c->kr_deep) { kc = 64; sr = 4; }
+    else if (ring(64, 3) <= (size_t)lim && forced != 32 && forced != 16) { kc = 64; sr = 3; }
+    else if (ring(32, 4) <= (size_t)lim && forced != 16) { kc = 32; sr = 4; }
+    else { kc = 16; sr = 4; }
+    const size_t smem = ring(kc, sr);
+    if (smem > (size_t)lim) return MPST_OK;
 #define KR_ARGS c, xl, xr, L, R, d, chi_l, chi_r, cls_begin, cls_end, ncls, G, smem
-    if (d % 6 == 0) {
-        *handled = true;
-        if (kc == 64) return launch_kr<1, 6, 1, 6, 8, 64, 3>(KR_ARGS);
-        if (kc == 32) return launch_kr<1, 6, 1, 6, 8, 32, 4>(KR_ARGS);
-        return launch_kr<1, 6, 1, 6, 8, 16, 4>(KR_ARGS);
-    }
-    if (d % 4 == 0) {
-        *handled = true;
-        if (kc == 64) return launch_kr<2, 4, 1, 4, 8, 64, 3>(KR_ARGS);
-        if (kc == 32) return launch_kr<2, 4, 1, 4, 8, 32, 4>(KR_ARGS);
-        return launch_kr<2, 4, 1, 4, 8, 16, 4>(KR_ARGS);
-    }
+#define KR_DISPATCH(MA_, S_, NB_, T_)                                                                   \
+    do {                                                                                                \
+        *handled = true;                                                                                \
+        if (kc == 64 && sr == 4) return launch_kr<MA_, S_, NB_, T_, 8, 64, 4>(KR_ARGS);                 \
+        if (kc == 64) return launch_kr<MA_, S_, NB_, T_, 8, 64, 3>(KR_ARGS);                            \
+        if (kc == 32 && sr == 6) return launch_kr<MA_, S_, NB_, T_, 8, 32, 6>(KR_ARGS);                 \
+        if (kc == 32) return launch_kr<MA_, S_, NB_, T_, 8, 32, 4>(KR_ARGS);                            \
+        return launch_kr<MA_, S_, NB_, T_, 8, 16, 4>(KR_ARGS);                                          \
+    } while (0)
+    if (d % 6 == 0) KR_DISPATCH(1, 6, 1, 6);
+    if (d % 4 == 0) KR_DISPATCH(2, 4, 1, 4);
+#undef KR_DISPATCH
 #undef KR_ARGS
     return MPST_OK;
 }

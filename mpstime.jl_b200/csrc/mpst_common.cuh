@@ -54,7 +54,7 @@ enum {
     L_SVD_ITERS,       // subspace iterations of the last split
     L_SVD_RESTARTS,    // restarts without the column-scaling shortcut
     L_GRAD_KERNEL,     // 1 bond_grad_kr_kernel (register operands), 2 bond_grad_kernel (shared-memory tiles)
-    L_GRAD_VARIANT,    // kr: MA*1000 + S*100 + KC;  tiles: TP*1000 + TQ
+    L_GRAD_VARIANT,    // kr: MA*10000 + S*1000 + KC*10 + SR;  tiles: TP*1000 + TQ
     L_KRAO_KERNEL,     // 1 krao_reg_kernel, 2 krao_gemm_kernel
     L_KRAO_VARIANT,    // reg: NI;  tiles: TN
     L_FWD_PATH,        // 1 factorised + cached environment, 2 factorised, 3 dense
@@ -119,6 +119,7 @@ struct mpst_ctx {
     std::vector<SegTable> segtabs;   // stream-K schedules, built once per shape (no per-bond host work / sync)
     uint64_t seg_clock = 0;
     EncTable enc;
+    int kr_deep = 1;            // 1: prefer the 64-sample x 4-stage ring of the register-operand gradient kernel where it fits
     int flag[F_COUNT] = {0};
     int last[L_COUNT] = {0};
     // cursor of mpst_sweep_bonds: next bond of the (backward, forward) cycle, -1 = not started

@@ -536,7 +536,8 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         mode = 2;
         // measured on trained bonds (k = 40): p = 80 with 5 iterations beats p = 96 with 4 and p = 112 with 3 --
         // the p^3 single-CTA kernels (Cholesky, Rayleigh-Ritz eigen-solver) dominate, not the GEMMs
-        p = std::min((int)round_up(2 * k + c->flag[F_SVD_OVS], 16), PMAX);
+        // p = 2k, but never fewer than 32 oversampling columns (k < 32: config A's chi = 20, the micro-sweep's chi = 16)
+        p = std::min(std::max((int)round_up(2 * k + c->flag[F_SVD_OVS], 16), (int)round_up(k + 32, 16)), PMAX);
         if (p < k + 32 || n <= p || m < p) return MPST_OK;            // too little oversampling: full Jacobi
     }
     const size_t need = (size_t)2 * n * p + (size_t)2 * m * p + (size_t)(MAXSPLIT + 4) * p * p + (size_t)n * k +

@@ -10,17 +10,23 @@ the reference file:line it follows (paths relative to /root/reference/src).
 
 Parity status
 -------------
-* Legendre encoding values and the RobustSigmoid->MinMax normalisation are PINNED against the
-  reference's own serialized output (`test/Data/ecg200/mps_saves/test_dataset.jld2`,
-  extracted by `tests/golden/make_golden_from_jld2.py` into `tests/golden/ecg200_legendre.npz`).
-* The training step (loss/grad, TSGO, SVD split, env update) and the imputation step follow the
-  reference source line by line, but the reference's known-answer tests for them
-  (`test/classification.jl:26,47`, `test/imputation.jl:34-52`) need the UCR downloads and a
-  missing blob, and three of the arithmetic pieces live in un-vendored Julia packages
-  (ITensors 0.6.22 / NDTensors 0.3.74 `svd`+`truncate!`, NumericalIntegration 0.2.0
-  `cumul_integrate`, Normalization 0.7.3) whose published algorithms are restated here:
-  **for those rows: parity unpinned** (self-consistency checks only: gradient vs finite
-  differences, loop-literal vs vectorised forms, legacy-formula cross-check).
+PINNED against the reference's own serialized output (`test/Data/ecg200/mps_saves/test_dataset.jld2`, the only
+artefact under /root/reference that holds numbers of this path; extracted by `tests/golden/make_golden_from_jld2.py`
+-> `ecg200_legendre.npz` and `tests/golden/make_golden_mps_from_jld2.py` -> `ecg200_trained_mps.npz`):
+* the RobustSigmoid -> MinMax normalisation and the Legendre encoding values (max deviation 2e-15);
+* the core index order (left link, site, right link[, class]), the label position, `contract_mps` / `classify`
+  (the reference's trained MPS classifies the reference's own encoded training set 100/100 through `overlaps`),
+  `normalize!` (<W|W> = 1 to 1e-15) and the canonical form a sweep leaves behind: sites 1..T-1 left-orthonormal (U of
+  `decomposeBT`), the label core's Gram matrix diagonal with descending entries (V*S, LAPACK ordering)
+  (tests/test_oracle.py::test_reference_trained_mps_pins_layout_norm_and_classification).
+PARITY UNPINNED (no replayable reference output exists: `test/classification.jl:26,47`, `test/imputation.jl:34-52` need
+the UCR downloads and a missing blob; the arithmetic lives in un-vendored Julia packages whose published algorithms
+are restated -- ITensors 0.6.22 / NDTensors 0.3.74 `svd` + `truncate!`, NumericalIntegration 0.2.0 `cumul_integrate`,
+Normalization 0.7.3, StatsBase 0.34.4 weighted `median`, KernelDensity / Interpolations for the data-driven bases):
+the per-bond loss / gradient values, the TSGO / GD update, the truncation rule's cutoff decision, the environment
+update, and the imputation step (median / mean / mode / ITS, WMAD, rejection, backwards order).  These follow the
+reference source line by line and are self-checked (literal loop == vectorised form, gradient == finite differences,
+backwards == forwards on the mirrored chain, C restatement == numpy).
 
 Conventions (0-based sites j = 0..T-1)
 --------------------------------------
