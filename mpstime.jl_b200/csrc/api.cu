@@ -216,7 +216,8 @@ const FlagDef kFlags[F_COUNT] = {
     {"SVD_DEBUG", 0, true}, {"SVD_SKIP", 0, false}, {"SVD_FIXED", 0, false}, {"SVD_FULL", 0, true},
     {"SVD_PB64", 0, true}, {"SVD_LEGACY", 0, true}, {"SVD_NOSUB", 0, true}, {"SVD_OVS", 0, false},
     {"SVD_NOHALF", 0, true}, {"SVD_HALF_FROM", 1, false}, {"SVD_IT", 0, false}, {"SVD_NOGRAPH", 0, true},
-    {"GRAD_KC", 0, false}, {"IMPUTE_NOSERIES", 0, true}, {"IMPUTE_FULLSYM", 0, true},
+    {"GRAD_KC", 0, false}, {"IMPUTE_NOSERIES", 0, true}, {"IMPUTE_FULLSYM", 0, true}, {"GRAD_PHASES", 0, false},
+    {"SVD_EIGSMEM", 0, true},
 };
 const char* kLast[L_COUNT] = {"svd_path", "svd_iters", "svd_restarts", "grad_kernel", "grad_variant", "krao_kernel",
                               "krao_variant", "fwd_path", "krao_reg_mask", "grad_kr_launches", "grad_tile_launches", "svd_calls",

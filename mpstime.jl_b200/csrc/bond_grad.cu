@@ -20,6 +20,7 @@
 #include <vector>
 #include "mpst_common.cuh"
 #include "dmma.cuh"
+#include "streamk.h"
 
 namespace {
 // CTA tile TP x TQ = (32*MI) x (16*NI): 8 warps as 4 (p) x 2 (q), warp tile (8*MI) x (8*NI).
@@ -254,48 +255,19 @@ int launch_bond_grad(mpst_ctx* c, const double* xl, const double* xr, const doub
         return MPST_OK;
     }
     // The schedule depends only on (tile shape, tile counts, class chunk ranges): built once, kept on the device
-    std::vector<int64_t> key = {2, TP, TQ, KC, ncta, ntp, ntq, ncls};
+    const int phases = c->flag[F_GRAD_PHASES];
+    std::vector<int64_t> key = {2, TP, TQ, KC, ncta, ntp, ntq, ncls, phases};
     for (int k = 0; k < ncls; k++) { key.push_back(cb[k]); key.push_back(ce[k]); }
     SegTable* tab = segtable_find(c, key);
     if (!tab) {
         std::vector<GradSeg> hsegs;
-        std::vector<int> hcta(ncta + 1, 0), hslot(ntiles + 1, 0);
-        // linear work space: tile-major, chunks within the tile
-        int64_t pos = 0;      // global chunk cursor
-        int cta = 0;
-        int64_t cta_end = (total * (cta + 1)) / ncta;
+        std::vector<int> hcta, hslot;
+        std::vector<std::array<int, 3>> units;
         for (int tile = 0; tile < ntiles; tile++) {
-            const int cls = tile / (ntp * ntq);
-            const int rem = tile - cls * ntp * ntq;
-            const int tp = rem / ntq, tq = rem - tp * ntq;
-            hslot[tile] = (int)hsegs.size();
-            int64_t j = cb[cls];
-            while (j < ce[cls]) {
-                while (pos >= cta_end && cta < ncta - 1) {           // advance to the CTA owning `pos`
-                    cta++;
-                    hcta[cta] = (int)hsegs.size();
-                    cta_end = (total * (cta + 1)) / ncta;
-                }
-                const int64_t take = std::min<int64_t>(ce[cls] - j, cta_end - pos);
-                GradSeg sgm;
-                sgm.cls = cls; sgm.tp = tp; sgm.tq = tq; sgm.slot = (int)hsegs.size();
-                sgm.chunk_begin = j; sgm.chunk_end = j + take;
-                hsegs.push_back(sgm);
-                j += take;
-                pos += take;
-            }
+            const int rem = tile % (ntp * ntq);
+            units.push_back({tile / (ntp * ntq), rem / ntq, rem % ntq});
         }
-        hslot[ntiles] = (int)hsegs.size();
-        while (cta < ncta) { cta++; hcta[cta] = (int)hsegs.size(); }
-        // L2 sharing: a CTA's contiguous range usually ends one pass over the samples and begins the next one at chunk 0.
-        // Walking its segments in ascending chunk order makes every CTA start at the first samples and move through the
-        // data set together (two fronts a fixed distance apart), so the raw rows one CTA pulls from HBM are L2 hits for
-        // the others -- without it each of the ~64 output groups streamed the whole data set from DRAM on its own
-        // (ncu: 54x the algorithmic bytes at the north-star shape).  Slots keep their table position, so the fixed-order
-        // segment reduction is unchanged.
-        for (int i = 0; i < ncta; i++)
-            std::stable_sort(hsegs.begin() + hcta[i], hsegs.begin() + hcta[i + 1],
-                             [](const GradSeg& a, const GradSeg& b) { return a.chunk_begin < b.chunk_begin; });
+        build_streamk_table(ncta, phases, units, cb, ce, hsegs, hcta, hslot);
         TRY(segtable_add(c, key, hsegs, hcta, hslot, &tab));
     }
     const int nseg = tab->nseg;

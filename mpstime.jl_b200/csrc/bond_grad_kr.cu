@@ -16,6 +16,7 @@
 #include <vector>
 #include "mpst_common.cuh"
 #include "dmma.cuh"
+#include "streamk.h"
 
 namespace {
 // KC = samples per pipeline stage, SR = raw stages: 64 x 3 where the ring fits in shared memory (config B:
@@ -234,44 +235,16 @@ int launch_kr(mpst_ctx* c, const double* xl, const double* xr, const double* L, 
         return MPST_OK;
     }
     // The schedule depends only on (kernel variant, group count, class chunk ranges): built once, kept on the device
-    std::vector<int64_t> key = {1, MA, S, NB, T, NW, KC, SR, ncta, geo.ngroups, ncls};
+    const int phases = c->flag[F_GRAD_PHASES];
+    std::vector<int64_t> key = {1, MA, S, NB, T, NW, KC, SR, ncta, geo.ngroups, ncls, phases};
     for (int k = 0; k < ncls; k++) { key.push_back(cb[k]); key.push_back(ce[k]); }
     SegTable* tab = segtable_find(c, key);
     if (!tab) {
         std::vector<GradSeg> hsegs;
-        std::vector<int> hcta(ncta + 1, 0), hslot(ngrp_total + 1, 0);
-        int cta = 0;
-        int64_t pos = 0, cta_end = total / ncta;
-        for (int grp = 0; grp < ngrp_total; grp++) {
-            const int cls = grp / geo.ngroups, group = grp - cls * geo.ngroups;
-            hslot[grp] = (int)hsegs.size();
-            int64_t j = cb[cls];
-            while (j < ce[cls]) {
-                while (pos >= cta_end && cta < ncta - 1) {
-                    cta++;
-                    hcta[cta] = (int)hsegs.size();
-                    cta_end = (total * (cta + 1)) / ncta;
-                }
-                const int64_t take = std::min<int64_t>(ce[cls] - j, cta_end - pos);
-                GradSeg sgm;
-                sgm.cls = cls; sgm.tp = group; sgm.tq = 0; sgm.slot = (int)hsegs.size();
-                sgm.chunk_begin = j; sgm.chunk_end = j + take;
-                hsegs.push_back(sgm);
-                j += take;
-                pos += take;
-            }
-        }
-        hslot[ngrp_total] = (int)hsegs.size();
-        while (cta < ncta) { cta++; hcta[cta] = (int)hsegs.size(); }
-        // L2 sharing: a CTA's contiguous range usually ends one pass over the samples and begins the next one at chunk 0.
-        // Walking its segments in ascending chunk order makes every CTA start at the first samples and move through the
-        // data set together (two fronts a fixed distance apart), so the raw rows one CTA pulls from HBM are L2 hits for
-        // the others -- without it each of the ~64 output groups streamed the whole data set from DRAM on its own
-        // (ncu: 54x the algorithmic bytes at the north-star shape).  Slots keep their table position, so the fixed-order
-        // segment reduction is unchanged.
-        for (int i = 0; i < ncta; i++)
-            std::stable_sort(hsegs.begin() + hcta[i], hsegs.begin() + hcta[i + 1],
-                             [](const GradSeg& a, const GradSeg& b) { return a.chunk_begin < b.chunk_begin; });
+        std::vector<int> hcta, hslot;
+        std::vector<std::array<int, 3>> units;
+        for (int grp = 0; grp < ngrp_total; grp++) units.push_back({grp / geo.ngroups, grp % geo.ngroups, 0});
+        build_streamk_table(ncta, phases, units, cb, ce, hsegs, hcta, hslot);
         TRY(segtable_add(c, key, hsegs, hcta, hslot, &tab));
     }
     const int nseg = tab->nseg;

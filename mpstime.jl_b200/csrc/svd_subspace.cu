@@ -24,6 +24,7 @@ int launch_dgemm(mpst_ctx* c, int ta, int tb, int M, int N, int K, const double*
                  int64_t ldb, double* C, int64_t ldc);
 int launch_dgemm_splitk(mpst_ctx* c, int ta, int tb, int M, int N, int K, const double* A, int64_t lda, const double* B,
                         int64_t ldb, double* Cparts, int max_splits, int* splits_out);
+bool launch_sym_eig_reg(int p, const double* L, double* W, double* ev, int* status, cudaStream_t st);
 
 namespace {
 
@@ -678,7 +679,9 @@ restart:
         splits = 1;
         // H = L L^T (Cholesky in registers, breakdown -> status -> exact fallback), then Jacobi on the columns of L
         launch_chol_inv(p, Gm, splits, Ri, Lm, status, c->stream);
-        if (launch_sym_eig<true>(p, eig_smem, Lm, 1, p, Wm, ev, status, c->stream)) CUDA_TRY(c, cudaGetLastError());
+        // register-resident Jacobi (sym_eig_reg.cu) for p = 16k; the shared-memory solver otherwise / on request
+        if (c->flag[F_SVD_EIGSMEM] || !launch_sym_eig_reg(p, Lm, Wm, ev, status, c->stream))
+            if (launch_sym_eig<true>(p, eig_smem, Lm, 1, p, Wm, ev, status, c->stream)) CUDA_TRY(c, cudaGetLastError());
         c->launches++;
         ritz_trunc_kernel<<<1, 256, 0, c->stream>>>(ev, p, n, trace_dev, chi_max, cutoff, c->perm, ev + p, c->iscal);
         gather_cols_kernel<<<(p * k + 255) / 256, 256, 0, c->stream>>>(Wm, p, c->perm, k, Wk);

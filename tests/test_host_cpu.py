@@ -246,3 +246,13 @@ def test_options_refuse_what_the_device_path_does_not_implement(pkg):
         Xs, _ = pkg.transform_train_data(np.random.default_rng(0).standard_normal((7, 9)), o)
         a, b = pkg.preprocess.encoding_range(name)
         assert Xs.min() >= a - 1e-12 and Xs.max() <= b + 1e-12
+
+
+def test_streamk_schedule_builder(tmp_path):
+    """The gradient kernels' host-side stream-K schedule (csrc/streamk.h): every (unit, chunk) covered exactly once,
+    CTAs balanced to one chunk, slots contiguous per unit in ascending chunk order, for every walk order."""
+    exe = str(tmp_path / "streamk_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I/usr/local/cuda/include", "-x", "c++",
+                           os.path.join(ROOT, "tests", "cpp", "streamk_check.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "STREAMK_OK" in out.stdout, out.stdout + out.stderr

@@ -15,7 +15,10 @@ L = rng.standard_normal((N, chi)) / np.sqrt(chi); R = rng.standard_normal((N, ch
 B = rng.standard_normal(((d * chi) ** 2, 2)); B /= np.linalg.norm(B)
 ctx = m.Context(0)
 ref = None
-for v in variants + [-1]:
+phases = [int(p) for p in os.environ.get("PHASES", "").split(",") if p] or [None]
+for v, ph in [(v, ph) for v in variants + [-1] for ph in phases]:
+    if ph is not None:
+        ctx.debug_set("GRAD_PHASES", ph)
     ctx.debug_set("GRAD_NOKR", 1 if v < 0 else 0)
     ctx.debug_set("GRAD_KC", max(v, 0))
     try:
@@ -26,7 +29,7 @@ for v in variants + [-1]:
         ms, n, fl = ctx.profile_get()["grad_kernel"]; ctx.profile_enable(False)
         if ref is None:
             ref = G
-        print(f"variant {v:4d}: kernel {'kr' if ctx.debug_get('grad_kernel') == 1 else 'tiles'} {ctx.debug_get('grad_variant')}  "
+        print(f"variant {v:4d} phases {ph}: kernel {'kr' if ctx.debug_get('grad_kernel') == 1 else 'tiles'} {ctx.debug_get('grad_variant')}  "
               f"{fl / (ms * 1e-3) / 1e12:6.2f} TFLOP/s  ({ms / n:.3f} ms)  max|G - G0| {np.abs(G - ref).max():.2e}", flush=True)
     except Exception as e:
         print(f"variant {v}: {e}")
