@@ -191,13 +191,14 @@ def measured_hbm_peak():
 GRAD_KERNEL_NAMES = {1: "bond_grad_kr_kernel", 2: "bond_grad_kernel"}
 
 
-def kernel_traffic(name, d, chi):
+def kernel_traffic(name, d, chi, n_local):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-    kernel at this bond shape (profiles/kernel_traffic.json), or None when no capture exists for it."""
+    kernel at this bond shape (profiles/kernel_traffic.json keeps bytes per sample of the captured launch; the traffic
+    of these kernels is proportional to the sample count), or None when no capture exists for it."""
     try:
         tab = json.load(open(TRAFFIC_FILE))
         e = tab.get(f"{name}:d{d}:chi{chi}")
-        return (float(e["bytes_per_launch"]), e["source"]) if e else (None, "no ncu capture for this kernel/shape")
+        return (float(e["bytes_per_sample"]) * n_local, e["source"]) if e else (None, "no ncu capture for this kernel/shape")
     except Exception:
         return None, "profiles/kernel_traffic.json missing"
 
@@ -445,6 +446,9 @@ def run_training(m, ctx, w, args, rank, world, local, td, steps, warmup, fp64_pe
     ctx.profile_reset()
     ctx.debug_set("grad_kr_launches", 0)
     ctx.debug_set("grad_tile_launches", 0)
+    SVD_KEYS = ("svd_calls", "svd_iters_sum", "svd_round2", "svd_jacobi", "svd_fast")
+    for k in SVD_KEYS:
+        ctx.debug_set(k, 0)
     clocks = ClockSampler(local)
     barrier(td, local)
     if rank == 0:
@@ -466,6 +470,7 @@ def run_training(m, ctx, w, args, rank, world, local, td, steps, warmup, fp64_pe
     n_kr, n_tile = ctx.debug_get("grad_kr_launches"), ctx.debug_get("grad_tile_launches")
     grad_kernel = GRAD_KERNEL_NAMES[1 if n_kr >= n_tile else 2]          # the kernel that ran most of the timed launches
     grad_mix = {"bond_grad_kr_kernel": n_kr, "bond_grad_kernel": n_tile}
+    svd_stats = {k: ctx.debug_get(k) for k in SVD_KEYS}
     ms = reduce_over_ranks(td, local, ms)
     sample_bonds = steps * bps * N_global
     value = sample_bonds / (ms * 1e-3)
@@ -504,7 +509,7 @@ def run_training(m, ctx, w, args, rank, world, local, td, steps, warmup, fp64_pe
         return None, cores_host, (Xs_sorted, counts)
     gk_ms, gk_n, gk_fl = prof["grad_kernel"]
     achieved = gk_fl / (gk_ms * 1e-3) / 1e12 if gk_ms > 0 else 0.0
-    traffic, traffic_src = kernel_traffic(grad_kernel, d, chi_max)
+    traffic, traffic_src = kernel_traffic(grad_kernel, d, chi_max, N_local)
     roofline = {"bound": "tensor", "kernel": grad_kernel, "kernel_launch_mix": grad_mix, "achieved": achieved,
                 "peak": fp64_peak[0], "unit": "TFLOP/s", "frac": achieved / fp64_peak[0], "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": fp64_peak[1], "launches": gk_n,
@@ -527,6 +532,8 @@ def run_training(m, ctx, w, args, rank, world, local, td, steps, warmup, fp64_pe
         "clocks": clk, "gpu_launches": int(launches),
         "roofline": roofline, "device_time_breakdown_ms": breakdown, "wall_s_timed": wall,
         "ms_per_bond": ms / (steps * bps),
+        "svd_stats": dict(svd_stats, note="timed region: splits, subspace iterations summed over the fast-path splits, splits that "
+                                          "needed a second round of iterations, exact-Jacobi fallbacks, fast-path splits"),
     }
     if e2e is not None:
         out["e2e"] = e2e
@@ -599,7 +606,7 @@ def main():
             ob, _, _ = run_training(m, ctx, dict(WORKLOADS["B"]), args, rank, world, local, td, steps=3, warmup=2,
                                     fp64_peak=fp64_peak, do_e2e=True)
             out["config_B"] = {k: ob[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "roofline", "e2e",
-                                                  "device_time_breakdown_ms", "ms_per_bond", "gpu_launches")}
+                                                  "device_time_breakdown_ms", "ms_per_bond", "gpu_launches", "svd_stats")}
         except Exception as e:
             out["config_B"] = {"value": None, "error": repr(e)}
 

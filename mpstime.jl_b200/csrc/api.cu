@@ -31,6 +31,7 @@ int launch_bond_grad_kr(mpst_ctx* c, const double* xl, const double* xr, const d
                         bool* handled);
 int launch_dgemm(mpst_ctx* c, int ta, int tb, int M, int N, int K, const double* A, int64_t lda, const double* B,
                  int64_t ldb, double* C, int64_t ldc);
+int svd_split_prepare(mpst_ctx* c, int Dl, int Dr, int C, int going_left, int chi_max, double cutoff, const double* norm2_dev);
 int svd_split_device(mpst_ctx* c, const double* B, int Dl, int Dr, int C, int going_left, int chi_max,
                      double cutoff, const double* norm2_dev, double* label_core, double* ortho_core,
                      int* chi_new, double* sigma_host, int* sweeps_out);
@@ -217,7 +218,7 @@ const FlagDef kFlags[F_COUNT] = {
     {"SVD_PB64", 0, true}, {"SVD_LEGACY", 0, true}, {"SVD_NOSUB", 0, true}, {"SVD_OVS", 0, false},
     {"SVD_NOHALF", 0, true}, {"SVD_HALF_FROM", 1, false}, {"SVD_IT", 0, false}, {"SVD_NOGRAPH", 0, true},
     {"GRAD_KC", 0, false}, {"IMPUTE_NOSERIES", 0, true}, {"IMPUTE_FULLSYM", 0, true}, {"GRAD_PHASES", 0, false},
-    {"SVD_EIGSMEM", 0, true},
+    {"SVD_EIGSMEM", 0, true}, {"SVD_SERIAL", 0, true}, {"SVD_CHOLSEQ", 0, true}, {"SVD_PROBE", 0, true}, {"SVD_SYNCFIRST", 0, true}, {"SVD_NOPREP", 0, true},
 };
 const char* kLast[L_COUNT] = {"svd_path", "svd_iters", "svd_restarts", "grad_kernel", "grad_variant", "krao_kernel",
                               "krao_variant", "fwd_path", "krao_reg_mask", "grad_kr_launches", "grad_tile_launches", "svd_calls",
@@ -290,6 +291,10 @@ int mpst_create(mpst_ctx** out, int device_id) {
     if (prop.major < 10) { delete c; return MPST_E_UNSUPPORTED; }               // sm_100a only
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { c->stream = nullptr; delete c; return MPST_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming) != cudaSuccess) { mpst_destroy(c); return MPST_E_CUDA; }
     const size_t maxn = (size_t)MPST_MAX_D * MPST_MAX_CHI + 64;
     bool ok = cudaMalloc(&c->scal, 32 * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMemset(c->scal, 0, 32 * sizeof(double)) == cudaSuccess;
@@ -313,16 +318,19 @@ int mpst_create(mpst_ctx** out, int device_id) {
 int mpst_destroy(mpst_ctx* c) {
     if (!c) return MPST_OK;
     cudaSetDevice(c->device);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     if (c->stream) cudaStreamSynchronize(c->stream);
     prof_drain(c);
     for (auto e : c->evpool) cudaEventDestroy(e);
     if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
+    for (auto& g : c->svd_graphs) if (g.exec) cudaGraphExecDestroy((cudaGraphExec_t)g.exec);
+    c->svd_graphs.clear();
     for (auto& t : c->segtabs) { cudaFree(t.segs); cudaFree(t.cta_ptr); cudaFree(t.tile_slot); }
     c->segtabs.clear();
     free_training(c, true);
     auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(c->B); fr(c->G); fr(c->Z); fr(c->part); fr(c->red); fr(c->scal); fr(c->S); fr(c->gpart); fr(c->wbuf);
-    fr(c->colnorm); fr(c->tmp); fr(c->meta); fr(c->sub); fr(c->gws);
+    fr(c->colnorm); fr(c->tmp); fr(c->meta); fr(c->sub); fr(c->gws); fr(c->gws2);
     if (c->enc.ip) cudaFree(c->enc.ip);
     if (c->enc.dp) cudaFree(c->enc.dp);
     for (int i = 0; i < 16; i++) if (c->imp_ptr[i]) cudaFree(c->imp_ptr[i]);
@@ -333,6 +341,10 @@ int mpst_destroy(mpst_ctx* c) {
     if (c->hscal) cudaFreeHost(c->hscal);
     if (c->hiscal) cudaFreeHost(c->hiscal);
     if (c->nccl_comm && g_nccl.destroy) g_nccl.destroy(c->nccl_comm);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_upload) cudaEventDestroy(c->ev_upload);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return MPST_OK;
@@ -404,6 +416,7 @@ static int model_reset(mpst_ctx* c, int T, int C, int d, int chi_max) {
     c->svd_its.clear();
     c->svd_hint_m = c->svd_hint_n = c->svd_hint_its = c->svd_hint_floor = 0;
     c->svd_floor.clear();
+    c->svd_calm.clear();
     c->svd_nohalf.clear();
     if ((int)c->cores.size() != T) {
         for (auto& k : c->cores) if (k.dev) cudaFree(k.dev);
@@ -819,6 +832,14 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         }
         TRY(loss_grad_device(c, phl, phr, L, R, chi_l, chi_r, c->B, c->G, o->loss_kind, o->train_sep, s_loss, coff_dev, denom_dev,
                              factored ? &kl : nullptr, factored ? &kr : nullptr, cached));
+        if (it == o->update_iters - 1) {
+            // the gradient kernel is running and the host has nothing to do: get the CUDA graph of this bond's split ready
+            if ((int)c->svd_its.size() != c->T) { c->svd_its.assign(c->T, 0); c->svd_floor.assign(c->T, 0); c->svd_calm.assign(c->T, 0); c->svd_nohalf.assign(c->T, 0); }
+            c->svd_slot = l;
+            const int rcp = svd_split_prepare(c, Dl, Dr, C, going_left, o->chi_max, o->cutoff, o->rescale_after ? s_bn2 : nullptr);
+            c->svd_slot = -1;
+            TRY(rcp);
+        }
         TRY(allreduce_sum(c, c->G, D * C + 1));
         ProfScope ps(c, MPST_T_UPDATE);
         TRY(launch_sumsq(c, c->G, D * C, s_gn2));
@@ -849,7 +870,7 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         const size_t cap = (size_t)d * c->chi_max * c->chi_max * C;
         TRY(core_reserve(c, klabel, cap));
         TRY(core_reserve(c, kortho, cap));
-        if ((int)c->svd_its.size() != c->T) { c->svd_its.assign(c->T, 0); c->svd_floor.assign(c->T, 0); c->svd_nohalf.assign(c->T, 0); }
+        if ((int)c->svd_its.size() != c->T) { c->svd_its.assign(c->T, 0); c->svd_floor.assign(c->T, 0); c->svd_calm.assign(c->T, 0); c->svd_nohalf.assign(c->T, 0); }
         c->svd_slot = l;
         const int rc_svd = svd_split_device(c, c->B, Dl, Dr, C, going_left, o->chi_max, o->cutoff, norm2_dev, klabel.dev,
                                             kortho.dev, &chi_new, nullptr, nullptr);
@@ -1198,7 +1219,12 @@ int mpst_bond_split(mpst_ctx* c, const double* B, int d, int chi_l, int chi_r, i
     CUDA_TRY(c, cudaMalloc(&dlab, (size_t)m * kmax * sizeof(double)));
     CUDA_TRY(c, cudaMalloc(&dort, (size_t)n * kmax * sizeof(double)));
     CUDA_TRY(c, cudaMemcpyAsync(dB, B, D * C * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    int rc = svd_split_device(c, dB, Dl, Dr, C, going_left, chi_max, cutoff, nullptr, dlab, dort, chi_new, sigma, nullptr);
+    int rc = svd_split_prepare(c, Dl, Dr, C, going_left, chi_max, cutoff, nullptr);      // while the copy is in flight
+    if (c->flag[F_SVD_SYNCFIRST]) cudaStreamSynchronize(c->stream);                       // probe: idle GPU at the start, as in a sweep
+    if (rc == MPST_OK) {
+        ProfScope ps(c, MPST_T_SVD);
+        rc = svd_split_device(c, dB, Dl, Dr, C, going_left, chi_max, cutoff, nullptr, dlab, dort, chi_new, sigma, nullptr);
+    }
     if (rc == MPST_OK) {
         const int k = *chi_new;
         // device: label core [c][x + Dx*k] (x = s + d*link), ortho core [y + n*k]  ->  wire layouts

@@ -109,9 +109,14 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ parts, int split
 // C = op(A) * op(B); ta/tb: 0 = as stored (column-major), 1 = transposed.
 // The subspace SVD's products are tiny next to the machine (tens of MFLOP) but long in K: when the output tiles
 // cover less than half of the SMs the K loop is split across CTAs and the partials are summed in a fixed order.
-int launch_dgemm(mpst_ctx* c, int ta, int tb, int M, int N, int K, const double* A, int64_t lda, const double* B,
-                 int64_t ldb, double* C, int64_t ldc) {
+// lane 0: the context's main stream and split-K workspace; lane 1: the side stream (own workspace), used by the
+// subspace SVD to run the small Gram / Cholesky chain next to the big product of the same iteration.
+int launch_dgemm_on(mpst_ctx* c, int lane, int ta, int tb, int M, int N, int K, const double* A, int64_t lda,
+                    const double* B, int64_t ldb, double* C, int64_t ldc) {
     if (M <= 0 || N <= 0) return MPST_OK;
+    cudaStream_t st = lane ? c->stream2 : c->stream;
+    double** ws = lane ? &c->gws2 : &c->gws;
+    size_t* wscap = lane ? &c->gws2cap : &c->gwscap;
     const int64_t sai = ta ? lda : 1, sak = ta ? 1 : lda;
     const int64_t sbk = tb ? ldb : 1, sbj = tb ? 1 : ldb;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
@@ -120,18 +125,23 @@ int launch_dgemm(mpst_ctx* c, int ta, int tb, int M, int N, int K, const double*
     if (splits >= 2) {
         const int kper = (nk + splits - 1) / splits;
         splits = (nk + kper - 1) / kper;
-        if (ensure_buf(c, &c->gws, &c->gwscap, (size_t)splits * M * N) != MPST_OK) return MPST_E_CUDA;
+        if (ensure_buf(c, ws, wscap, (size_t)splits * M * N) != MPST_OK) return MPST_E_CUDA;
         grid.z = splits;
-        dgemm_kernel<<<grid, 256, 0, c->stream>>>(A, sai, sak, B, sbk, sbj, c->gws, M, M, N, K, kper, (int64_t)M * N);
-        splitk_reduce_kernel<<<(unsigned)(((int64_t)M * N + 255) / 256), 256, 0, c->stream>>>(c->gws, splits, M, N, C, ldc);
+        dgemm_kernel<<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, *ws, M, M, N, K, kper, (int64_t)M * N);
+        splitk_reduce_kernel<<<(unsigned)(((int64_t)M * N + 255) / 256), 256, 0, st>>>(*ws, splits, M, N, C, ldc);
         c->launches += 2;
         CUDA_TRY(c, cudaGetLastError());
         return MPST_OK;
     }
-    dgemm_kernel<<<grid, 256, 0, c->stream>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, nk, 0);
+    dgemm_kernel<<<grid, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, nk, 0);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
     return MPST_OK;
+}
+
+int launch_dgemm(mpst_ctx* c, int ta, int tb, int M, int N, int K, const double* A, int64_t lda, const double* B,
+                 int64_t ldb, double* C, int64_t ldc) {
+    return launch_dgemm_on(c, 0, ta, tb, M, N, K, A, lda, B, ldb, C, ldc);
 }
 
 // split-K variant: `splits` partial products, partial z at C + z*M*N (ldc = M).  Returns the split count used.

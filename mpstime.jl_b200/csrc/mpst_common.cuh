@@ -45,7 +45,7 @@ struct Timer {
 enum {
     F_DENSE_FWD = 0, F_NO_ENV_REUSE, F_GRAD_T128, F_GRAD_NOKR, F_IMPUTE_NODBUF, F_IMPUTE_DEBUG, F_KRAO_NOREG,
     F_SVD_INNER, F_SVD_DEBUG, F_SVD_SKIP, F_SVD_FIXED, F_SVD_FULL, F_SVD_PB64, F_SVD_LEGACY, F_SVD_NOSUB, F_SVD_OVS,
-    F_SVD_NOHALF, F_SVD_HALF_FROM, F_SVD_IT, F_SVD_NOGRAPH, F_GRAD_KC, F_IMPUTE_NOSERIES, F_IMPUTE_FULLSYM, F_GRAD_PHASES, F_SVD_EIGSMEM, F_COUNT
+    F_SVD_NOHALF, F_SVD_HALF_FROM, F_SVD_IT, F_SVD_NOGRAPH, F_GRAD_KC, F_IMPUTE_NOSERIES, F_IMPUTE_FULLSYM, F_GRAD_PHASES, F_SVD_EIGSMEM, F_SVD_SERIAL, F_SVD_CHOLSEQ, F_SVD_PROBE, F_SVD_SYNCFIRST, F_SVD_NOPREP, F_COUNT
 };
 // which code path the last call took (mpst_debug_get): lets the parity tests assert that they exercised the
 // kernels the benchmark runs, and lets bench.py name the kernel it reports a roofline for
@@ -82,6 +82,13 @@ struct SegTable {       // cached stream-K schedule of one (kernel variant, shap
     int* cta_ptr = nullptr;
     int* tile_slot = nullptr;
     int nseg = 0;
+    uint64_t last_use = 0;
+};
+
+struct SvdGraph {       // one captured round of the subspace SVD (svd_subspace.cu)
+    std::vector<int64_t> key;
+    void* exec = nullptr;        // cudaGraphExec_t
+    int64_t launches = 0;
     uint64_t last_use = 0;
 };
 
@@ -137,6 +144,12 @@ struct mpst_ctx {
     double* sub = nullptr;      // subspace-SVD workspace
     size_t subcap = 0;
     double* gws = nullptr;      // split-K partial products of the small GEMMs
+    double* gws2 = nullptr;     // ... of the GEMMs on the side stream
+    size_t gws2cap = 0;
+    cudaStream_t stream2 = nullptr;            // side stream of the subspace SVD (Gram + Cholesky next to the big product)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_upload = nullptr;
+    bool svd_prepare_only = false;             // svd_subspace_device: build / upload the round's CUDA graph, launch nothing
+    void* svd_uploaded = nullptr;              // graph exec whose upload is in flight on the side stream
     void* imp_ptr[16] = {nullptr};   // imputation work buffers (grow-only, reused across mpst_impute_batch calls)
     size_t imp_cap[16] = {0};
     // per-bond subspace-iteration count learned during training (svd_subspace.cu): svd_slot = bond being split
@@ -147,10 +160,11 @@ struct mpst_ctx {
     std::vector<uint64_t> core_ver, env_ver, env_core_ver, env_src_ver;
     std::vector<int> env_dir;
     int svd_slot = -1;
-    std::vector<int> svd_its, svd_floor;
+    std::vector<int> svd_its, svd_floor, svd_calm;
     // iteration count proven on the most recently split bond of the same shape: a bond without history of its own starts
     // from its neighbour's count instead of the conservative default (spectra change slowly along the chain)
     int svd_hint_m = 0, svd_hint_n = 0, svd_hint_its = 0, svd_hint_floor = 0;
+    std::vector<SvdGraph> svd_graphs;
     std::vector<char> svd_nohalf;   // bonds on which the column-scaling shortcut of the subspace iteration broke down once
     // capacities (doubles) of the training buffers: a re-load with the same or a smaller shape reuses them
     size_t cap_X = 0, cap_PHI = 0, cap_phi = 0, cap_env = 0, cap_ones = 0, cap_yw = 0;

@@ -640,6 +640,26 @@ static int jacobi_sweeps_fused(mpst_ctx* c, int m, int n, int npad, int64_t ld, 
     return MPST_OK;
 }
 
+// Called while the gradient kernel of the same bond is still running: builds (first time) and uploads the CUDA graph
+// of the split's first subspace round, so that the split itself starts with a single cheap launch.  Must see the same
+// arguments as the svd_split_device call that follows; changes no numerical state.
+int svd_split_prepare(mpst_ctx* c, int Dl, int Dr, int C, int going_left, int chi_max, double cutoff, const double* norm2_dev) {
+    if (c->flag[F_SVD_NOPREP] || c->flag[F_SVD_NOGRAPH] || c->flag[F_SVD_DEBUG] || c->flag[F_SVD_NOSUB] || !c->stream2) return MPST_OK;
+    const int n = going_left ? Dr : Dl;
+    const int m = C * (going_left ? Dl : Dr);
+    const bool wide = c->flag[F_SVD_PB64] && n >= 256;
+    const int npad = (int)round_up(n, wide ? 64 : 32);
+    const int64_t ld = round_up(m + n, 2);
+    TRY(ensure_buf(c, &c->S, &c->Scap, (size_t)ld * npad));
+    const double* trace_dev = norm2_dev ? nullptr : c->scal + 5;
+    bool done = false;
+    int chi_dummy = 0;
+    c->svd_prepare_only = true;
+    const int rc = svd_subspace_device(c, c->S, ld, m, n, C, chi_max, cutoff, trace_dev, nullptr, nullptr, &chi_dummy, nullptr, &done);
+    c->svd_prepare_only = false;
+    return rc;
+}
+
 // B: [C][Dl*Dr] on the device.  Writes the two new cores into label_core / ortho_core (device,
 // capacity checked by the caller) and returns chi_new (host) after one small D2H copy.
 // norm2_dev != nullptr: B is scaled by 1/sqrt(*norm2_dev) on load (fused renormalisation).

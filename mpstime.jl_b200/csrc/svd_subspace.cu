@@ -18,12 +18,16 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <utility>
 #include "mpst_common.cuh"
 
 int launch_dgemm(mpst_ctx* c, int ta, int tb, int M, int N, int K, const double* A, int64_t lda, const double* B,
                  int64_t ldb, double* C, int64_t ldc);
 int launch_dgemm_splitk(mpst_ctx* c, int ta, int tb, int M, int N, int K, const double* A, int64_t lda, const double* B,
                         int64_t ldb, double* Cparts, int max_splits, int* splits_out);
+int launch_dgemm_on(mpst_ctx* c, int lane, int ta, int tb, int M, int N, int K, const double* A, int64_t lda,
+                    const double* B, int64_t ldb, double* C, int64_t ldc);
 bool launch_sym_eig_reg(int p, const double* L, double* W, double* ev, int* status, cudaStream_t st);
 
 namespace {
@@ -103,9 +107,10 @@ chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restr
         for (int cc = 0; cc < NRC; cc++)
             if (ty + TYN * r == tx + 16 * cc && ty + TYN * r < p) s_diag[ty + TYN * r] = m[r][cc];
     __syncthreads();
-    double tr = 0.0;
-    for (int i = 0; i < p; i++) tr = fmax(tr, s_diag[i]);
-    const double tiny = 1e-13 * tr;                    // kappa(G) beyond ~1e13: CholeskyQR no longer trustworthy
+    // A pivot is the squared norm of column k of the factored matrix after projecting out columns < k; relative to
+    // the column's own squared norm g_kk it is sin^2 of the angle to their span.  Below ~1e-13 CholeskyQR is no
+    // longer trustworthy.  The test is per column (Cholesky itself is invariant under column scaling), so graded
+    // columns -- norms spread over orders of magnitude but directions well separated -- pass.
     bool bad = false;
 #ifdef MPST_KDEBUG
     const long long tk0 = clock64();
@@ -130,8 +135,9 @@ chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restr
                 }
                 __syncthreads();                       // the only barrier of the step (row buffers alternate)
                 const double dk = rk[k];
+                const double tiny = 1e-13 * s_diag[k];
                 bad |= !(dk > tiny);
-                const double inv = rsqrt(dk > tiny ? dk : tiny);      // 1 / l_kk
+                const double inv = rsqrt(dk > tiny ? dk : fmax(tiny, 1e-300));      // 1 / l_kk
                 double li[NRR], rj[NRC];
 #pragma unroll
                 for (int r = krr; r < NRR; r++) {
@@ -174,9 +180,176 @@ chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restr
     if (threadIdx.x == 0 && bad) atomicOr(status, 1);
 }
 
+// Blocked form of chol_inv_kernel for p = 16 NRC: panels of 8 pivots.  The unblocked kernel pays one block barrier
+// and one dependent rsqrt chain per pivot (47 us at p = 112: ~825 cycles per pivot, 5x the FP64 work).  Here one warp
+// factors and inverts the 8 x 8 diagonal block in registers (the only serial part), 16 NRC threads form the panel
+//     P[:, x] = Lkk^-1 M[K, x]   (x outside the panel: column x of L^T below the panel / finished rows of X left of it)
+//     P[:, K] = Lkk^-1
+// and every thread applies the eight rank-1 updates m_ij -= P[t][i] P[t][j] from shared memory with no barrier in
+// between: three barriers per 8 pivots.  Same in-place layout as the unblocked kernel (trailing square = symmetric
+// Schur complement, dead L positions take X = L^-1), same per-column breakdown test.
+template <int NRC>
+__global__ void __launch_bounds__(256)
+chol_inv_blk_kernel(const double* __restrict__ G, double* __restrict__ Rinv, double* __restrict__ Lout,
+                    int* __restrict__ status) {
+    constexpr int P = 16 * NRC, PP = P + 4;
+    __shared__ double praw[8][PP];
+    __shared__ double pm[8][PP];
+    __shared__ __align__(16) double linv[8][8];
+    __shared__ double lkk[8][8];
+    __shared__ double s_diag[P];
+    __shared__ int s_bad;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double m[NRC][NRC];
+    if (threadIdx.x == 0) s_bad = 0;
+    // G is symmetric (same accumulation order in both triangles): the transposed, coalesced read is the same matrix
+#pragma unroll
+    for (int r = 0; r < NRC; r++)
+#pragma unroll
+        for (int cc = 0; cc < NRC; cc++) m[r][cc] = G[(size_t)P * (ty + 16 * r) + tx + 16 * cc];
+#pragma unroll
+    for (int r = 0; r < NRC; r++)
+#pragma unroll
+        for (int cc = 0; cc < NRC; cc++)
+            if (r == cc && ty == tx) s_diag[ty + 16 * r] = m[r][cc];
+    __syncthreads();
+#pragma unroll
+    for (int kp = 0; kp < 2 * NRC; kp++) {
+        const int k0 = 8 * kp, slot = kp >> 1, half = kp & 1;
+        const bool in_panel = (ty >> 3) == half;                 // this thread's row of slot `slot` is a pivot row
+        // (a) publish the 8 pivot rows (already updated by the previous panels)
+        if (in_panel) {
+#pragma unroll
+            for (int cc = 0; cc < NRC; cc++) praw[ty & 7][tx + 16 * cc] = m[slot][cc];
+        }
+        __syncthreads();
+        // (b) warp 0: Cholesky of the 8 x 8 diagonal block and its inverse, all lanes redundantly in registers
+        if (threadIdx.x < 32) {
+            double a[8][8], inv[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) a[i][j] = praw[i][k0 + j];
+            bool bad = false;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const double dk = a[k][k];
+                const double tiny = 1e-13 * s_diag[k0 + k];
+                bad |= !(dk > tiny);
+                inv[k] = rsqrt(dk > tiny ? dk : fmax(tiny, 1e-300));
+                a[k][k] = dk * inv[k];
+#pragma unroll
+                for (int i = k + 1; i < 8; i++) a[i][k] *= inv[k];
+#pragma unroll
+                for (int j = k + 1; j < 8; j++)
+#pragma unroll
+                    for (int i = j; i < 8; i++) a[i][j] = fma(-a[i][k], a[j][k], a[i][j]);
+            }
+            // inverse: lane k (< 8) forms column k of X = Lkk^-1 by forward substitution (x_j = 0 for j < k), with
+            // predicates instead of lane-dependent loop bounds so that every register index stays a constant
+            const int lane = threadIdx.x;
+            const int kc = lane & 7;
+            double xc[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int j = 0; j < i; j++) sacc = fma(a[i][j], xc[j], sacc);
+                xc[i] = i < kc ? 0.0 : (i == kc ? inv[i] : -sacc * inv[i]);
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) linv[i][kc] = xc[i];
+            }
+            if (lane == 8 && Lout != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) lkk[i][j] = j <= i ? a[i][j] : 0.0;
+            }
+            if (lane == 0 && bad) s_bad = 1;
+        }
+        __syncthreads();
+        // (c) the panel: one thread per column x
+        if (threadIdx.x < P) {
+            const int x = threadIdx.x;
+            const bool diag = x >= k0 && x < k0 + 8;
+            double v[8], o[8];
+#pragma unroll
+            for (int s = 0; s < 8; s++) v[s] = praw[s][x];
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int s = 0; s <= t; s++) acc = fma(linv[t][s], v[s], acc);
+                o[t] = diag ? linv[t][(x - k0) & 7] : acc;
+                pm[t][x] = o[t];
+            }
+            if (Lout != nullptr) {
+                if (x >= k0 + 8) {
+#pragma unroll
+                    for (int t = 0; t < 8; t++) Lout[x + (size_t)P * (k0 + t)] = o[t];
+                } else if (diag) {
+#pragma unroll
+                    for (int t = 0; t < 8; t++)
+                        if (t <= x - k0) Lout[x + (size_t)P * (k0 + t)] = lkk[x - k0][t];
+                }
+            }
+        }
+        __syncthreads();
+        // (d) rows of the panel take P; rows below take the eight rank-1 updates (columns of the panel: X = -L_iK Lkk^-1)
+        const bool cpan = (tx >> 3) == half;                     // this thread's column of slot `slot` is a panel column
+#pragma unroll
+        for (int r = slot; r < NRC; r++) {
+            if (r == slot && in_panel) {
+#pragma unroll
+                for (int cc = 0; cc < NRC; cc++) m[r][cc] = pm[ty & 7][tx + 16 * cc];
+            } else if (cpan && (r > slot || (ty >> 3) > half)) {
+                m[r][slot] = 0.0;                                // consumed L entries: start of X_iK
+            }
+        }
+#pragma unroll 2
+        for (int t = 0; t < 8; t++) {
+            double li[NRC], rj[NRC];
+#pragma unroll
+            for (int r = slot; r < NRC; r++) {
+                const double vv = pm[t][ty + 16 * r];
+                li[r] = (r > slot || (ty >> 3) > half) ? vv : 0.0;       // rows at or above the panel do not move
+            }
+#pragma unroll
+            for (int cc = 0; cc < NRC; cc++) rj[cc] = pm[t][tx + 16 * cc];
+#pragma unroll
+            for (int r = slot; r < NRC; r++)
+#pragma unroll
+                for (int cc = 0; cc < NRC; cc++) m[r][cc] = fma(-li[r], rj[cc], m[r][cc]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < NRC; r++)
+#pragma unroll
+        for (int cc = 0; cc < NRC; cc++) {
+            const int i = ty + 16 * r, j = tx + 16 * cc;                  // Rinv[j + p*i] = X[i][j]  (i >= j)
+            Rinv[j + (size_t)P * i] = (i >= j) ? m[r][cc] : 0.0;
+        }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_bad) atomicOr(status, 1);
+}
+
 // p <= 96: 4 warps (8 x 16 threads, 2NC x NC register tile) -- these kernels are issue/latency bound and the
 // per-thread scalar preamble dominates, so fewer, fatter threads win; larger p: 8 warps (register budget).
-void launch_chol_inv(int p, const double* G, int splits, double* Rinv, double* Lout, int* status, cudaStream_t st) {
+void launch_chol_inv(int p, const double* G, int splits, double* Rinv, double* Lout, int* status, cudaStream_t st,
+                     bool blocked = true) {
+    if (blocked && splits == 1 && p % 16 == 0 && p >= 32 && p <= 128) {
+        switch (p / 16) {
+            case 2: chol_inv_blk_kernel<2><<<1, 256, 0, st>>>(G, Rinv, Lout, status); return;
+            case 3: chol_inv_blk_kernel<3><<<1, 256, 0, st>>>(G, Rinv, Lout, status); return;
+            case 4: chol_inv_blk_kernel<4><<<1, 256, 0, st>>>(G, Rinv, Lout, status); return;
+            case 5: chol_inv_blk_kernel<5><<<1, 256, 0, st>>>(G, Rinv, Lout, status); return;
+            case 6: chol_inv_blk_kernel<6><<<1, 256, 0, st>>>(G, Rinv, Lout, status); return;
+            case 7: chol_inv_blk_kernel<7><<<1, 256, 0, st>>>(G, Rinv, Lout, status); return;
+            default: chol_inv_blk_kernel<8><<<1, 256, 0, st>>>(G, Rinv, Lout, status); return;
+        }
+    }
     switch ((p + 15) / 16) {
         case 1: chol_inv_kernel<2, 1, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, Lout, status); break;
         case 2: chol_inv_kernel<4, 2, 8><<<1, 128, 0, st>>>(G, splits, p, Rinv, Lout, status); break;
@@ -541,7 +714,8 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         p = std::min(std::max((int)round_up(2 * k + c->flag[F_SVD_OVS], 16), (int)round_up(k + 32, 16)), PMAX);
         if (p < k + 32 || n <= p || m < p) return MPST_OK;            // too little oversampling: full Jacobi
     }
-    const size_t need = (size_t)2 * n * p + (size_t)2 * m * p + (size_t)(MAXSPLIT + 4) * p * p + (size_t)n * k +
+    if (c->svd_prepare_only && mode != 2) return MPST_OK;              // only the subspace rounds are graphs
+    const size_t need = (size_t)2 * n * p + (size_t)2 * m * p + (size_t)(MAXSPLIT + 4) * p * p + (size_t)2 * n * k +
                         (size_t)m * k + 4 * p + 64;
     TRY(ensure_buf(c, &c->sub, &c->subcap, need));
     double* Qa = c->sub;
@@ -555,11 +729,12 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     double* Lm = Wk + (size_t)p * p;                                   // Cholesky factor of the Ritz matrix
     double* T2 = Lm + (size_t)p * p;                                   // n x k
     double* Uk = T2 + (size_t)n * k;                                   // m x k
-    double* ev = Uk + (size_t)m * k;                                   // p, then Psorted p
+    double* Vs = Uk + (size_t)m * k;                                   // n x k staging block of V_k (subspace mode)
+    double* ev = Vs + (size_t)n * k;                                   // p, then Psorted p
     int* status = c->iscal + 8;
-    unsigned long long* resbits = reinterpret_cast<unsigned long long*>(c->scal + 10);
+    unsigned long long* resbits = reinterpret_cast<unsigned long long*>(c->iscal + 10);
     const size_t eig_smem = 2 * sizeof(double) * (size_t)p * (p + 1) + sizeof(double) * p + sizeof(int) * p + 16;
-    CUDA_TRY(c, cudaMemsetAsync(status, 0, sizeof(int), c->stream));
+    if (!c->svd_prepare_only) CUDA_TRY(c, cudaMemsetAsync(status, 0, sizeof(int), c->stream));
     const bool dbg = c->flag[F_SVD_DEBUG] != 0;
     if (dbg) cudaStreamSynchronize(c->stream);
     const auto t0 = std::chrono::steady_clock::now();
@@ -570,6 +745,7 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         c->last[L_SVD_ITERS] = iters;
         c->last[L_SVD_ITERS_SUM] += iters;
         c->last[L_SVD_FAST]++;
+        if (mode == 2) CUDA_TRY(c, cudaMemcpyAsync(ortho_core, Vs, sizeof(double) * (size_t)n * (*chi_new), cudaMemcpyDeviceToDevice, c->stream));
         scatter_label_kernel<<<2 * c->sm_count, 256, 0, c->stream>>>(Uk, m, m / C, c->iscal, label_core);
         c->launches++;
         CUDA_TRY(c, cudaGetLastError());
@@ -626,16 +802,11 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         // Gram matrix through the auto split-K GEMM (partials summed by a wide reduce kernel): the single-CTA
         // Cholesky then reads one p x p matrix instead of ~15 partials (its load phase was as long as its pivot loop)
         TRY(launch_dgemm(c, 1, 0, p, p, rows, X, rows, X, rows, Gm, p));
-        launch_chol_inv(p, Gm, 1, Ri, nullptr, status, c->stream);
+        launch_chol_inv(p, Gm, 1, Ri, nullptr, status, c->stream, !c->flag[F_SVD_CHOLSEQ]);
         c->launches++;
         TRY(launch_dgemm(c, 0, 0, rows, p, p, X, rows, Ri, p, out, rows));
         return MPST_OK;
     };
-    {
-        const int64_t tot = (int64_t)n * p;
-        rand_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(Qa, n, p, n, 0x5DEECE66Dull + (uint64_t)m * 131 + n);
-        c->launches++;
-    }
     // the random start needs no orthonormalisation: an n x p matrix of iid entries is well conditioned
     // (kappa ~ (sqrt(n)+sqrt(p))/(sqrt(n)-sqrt(p))) and only its span matters
     const int max_rounds = 3;
@@ -644,41 +815,97 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
     // instead of orthonormalised.  If that ever makes a Cholesky pivot break down on a bond, the bond is flagged and
     // this call restarts with full orthonormalisation, so the shortcut can cost time but never correctness.
     const int slot0 = (c->svd_slot >= 0 && c->svd_slot < (int)c->svd_its.size()) ? c->svd_slot : -1;
-    bool half_orth = slot0 >= 0 && !c->svd_nohalf[slot0] && !c->flag[F_SVD_NOHALF];
+    // a breakdown (rank-deficient bond early in training) sends the bond's next three visits down the serial loop with full
+    // orthonormalisation, then the shortcuts are tried again
+    if (slot0 >= 0 && c->svd_nohalf[slot0] > 0 && !c->svd_prepare_only) c->svd_nohalf[slot0]--;
+    const bool penalised = slot0 >= 0 && c->svd_nohalf[slot0] > (c->svd_prepare_only ? 1 : 0);
+    bool half_orth = slot0 >= 0 && !penalised && !c->flag[F_SVD_NOHALF];
     const int half_from = c->flag[F_SVD_HALF_FROM];
-restart:
-    for (int round = 0; round < max_rounds; round++) {
-        // iterations of the first round: 5 unless this bond's previous visits showed that fewer reach the residual
-        // bound (trained spectra change slowly from sweep to sweep); a visit that needs a second round raises the
-        // bond's floor for good, so every level is tried at most once per bond
-        const int slot = (c->svd_slot >= 0 && c->svd_slot < (int)c->svd_its.size()) ? c->svd_slot : -1;
-        int first = c->flag[F_SVD_IT] > 0 ? c->flag[F_SVD_IT] : (p >= 2 * k ? 5 : 7);
-        const bool hinted = slot >= 0 && c->svd_its[slot] == 0 && c->flag[F_SVD_IT] <= 0 && c->svd_hint_its > 0 &&
-                            c->svd_hint_m == m && c->svd_hint_n == n;
-        if (slot >= 0 && c->svd_its[slot] > 0 && c->flag[F_SVD_IT] <= 0) first = c->svd_its[slot];
-        else if (hinted) first = std::max(c->svd_hint_its, c->svd_floor[slot]);
-        const int niter = round == 0 ? first : 3;
-        for (int it = 0; it < niter; it++) {
-            TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, Qa, n, Za, m));            // Z = M Q
-            if (half_orth && iters_done >= half_from) {
+    // overlapped loop (default, also for the stand-alone mpst_bond_split): any Cholesky breakdown restarts the call in
+    // the serial form with full orthonormalisation of both blocks, and a training bond remembers it
+    bool overlap = !c->flag[F_SVD_SERIAL] && !c->flag[F_SVD_NOHALF] && c->stream2 != nullptr && !penalised;
+
+    // Everything one round puts on the stream(s), from the start block to the read-back of {chi_new, flags, status,
+    // residual}.  It touches only workspace buffers (V_k goes to the staging block `Vs`), so for a given shape and
+    // iteration count it is the same sequence of ~100 launches on every bond: it is captured once into a CUDA graph and
+    // replayed (one launch call instead of ~100; in a sweep the GPU is idle when the split starts and the host could
+    // not enqueue the small kernels as fast as they ran).  `fresh`: first round of a call (random start block).
+    auto enqueue_round = [&](bool fresh, int niter, int iters_before) -> int {
+        double* qa = Qa;
+        double* qb = Qb;
+        int itd = iters_before;
+        if (fresh) {
+            CUDA_TRY(c, cudaMemsetAsync(status, 0, sizeof(int), c->stream));
+            const int64_t tot = (int64_t)n * p;
+            rand_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(qa, n, p, n, 0x5DEECE66Dull + (uint64_t)m * 131 + n);
+            c->launches++;
+        }
+        if (overlap) {
+            // Overlapped form of the same iteration.  With Y_i = M^T M Q_{i-1} and Q_i = Y_i R_i^-1 (Cholesky-QR), the next
+            // block is Y_{i+1} = M^T M Q_i = (M^T (M Y_i)) R_i^-1: the two big products do not need R_i, so the Gram
+            // matrix and its Cholesky inverse (one SM, latency bound, as long as both products together) run on the
+            // side stream next to them and R_i^-1 is applied afterwards.  Q_i itself is only formed after the last
+            // iteration.  The left block Z is never re-orthonormalised (its columns are graded but well separated,
+            // and Cholesky does not care about column scales).
+            int todo = niter;
+            if (fresh) {
+                TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, qa, n, Za, m));        // Z = M Q0 (random start)
+                TRY(cholqr(Za, Zb, m));
+                TRY(launch_dgemm(c, 1, 0, n, p, m, M, ldm, Zb, m, qb, n));        // Y_1 = M^T orth(Z)
+            } else {
+                TRY(launch_dgemm(c, 1, 0, n, p, m, M, ldm, Za, m, qb, n));        // next round: Y = M^T (M Q) of the failed Rayleigh-Ritz
+            }
+            todo--;
+            for (; todo > 0; todo--) {
+                CUDA_TRY(c, cudaEventRecord(c->ev_fork, c->stream));
+                CUDA_TRY(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+                TRY(launch_dgemm_on(c, 1, 1, 0, p, p, n, qb, n, qb, n, Gm, p));   // side: G = Y^T Y, R^-1
+                launch_chol_inv(p, Gm, 1, Ri, nullptr, status, c->stream2, !c->flag[F_SVD_CHOLSEQ]);
+                c->launches++;
+                CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream2));
+                TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, qb, n, Za, m));        // main: M Y, M^T (M Y)
+                TRY(launch_dgemm(c, 1, 0, n, p, m, M, ldm, Za, m, qa, n));
+                CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+                TRY(launch_dgemm(c, 0, 0, n, p, p, qa, n, Ri, p, qb, n));         // Y_{i+1} = (M^T M Y_i) R_i^-1
+            }
+            TRY(cholqr(qb, qa, n));                                               // Q = orth(Y)
+        } else
+        for (int it = 0; it < niter; it++, itd++) {
+            TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, qa, n, Za, m));            // Z = M Q
+            if (half_orth && itd >= half_from) {
                 colscale_kernel<<<p, 256, 0, c->stream>>>(Za, Zb, m);
                 c->launches++;
             } else {
                 TRY(cholqr(Za, Zb, m));
             }
-            TRY(launch_dgemm(c, 1, 0, n, p, m, M, ldm, Zb, m, Qb, n));            // Y = M^T Z
-            TRY(cholqr(Qb, Qa, n));
-            iters_done++;
+            TRY(launch_dgemm(c, 1, 0, n, p, m, M, ldm, Zb, m, qb, n));            // Y = M^T Z
+            TRY(cholqr(qb, qa, n));
         }
-        TRY(cholqr(Qa, Qb, n));                                                    // second pass: orthonormal to rounding
-        CUDA_TRY(c, cudaMemcpyAsync(Qa, Qb, sizeof(double) * (size_t)n * p, cudaMemcpyDeviceToDevice, c->stream));
+        // second pass: orthonormal to rounding (the first pass leaves ||Q^T Q - I|| ~ eps kappa(Y)^2), and Z = M Q.
+        // The result always lands in Qa (the next round continues from it).
+        if (overlap) {
+            // Q1 is orthonormal to ~1e-9 already, so Z = M Q = (M Q1) R2^-1 loses nothing: the big product runs next to
+            // the Gram / Cholesky chain of the second pass
+            CUDA_TRY(c, cudaEventRecord(c->ev_fork, c->stream));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+            TRY(launch_dgemm_on(c, 1, 1, 0, p, p, n, qa, n, qa, n, Gm, p));
+            launch_chol_inv(p, Gm, 1, Ri, nullptr, status, c->stream2, !c->flag[F_SVD_CHOLSEQ]);
+            c->launches++;
+            CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream2));
+            TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, qa, n, Zb, m));            // M Q1
+            CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+            TRY(launch_dgemm(c, 0, 0, m, p, p, Zb, m, Ri, p, Za, m));             // Z = (M Q1) R2^-1
+            TRY(launch_dgemm(c, 0, 0, n, p, p, qa, n, Ri, p, qb, n));             // Q = Q1 R2^-1
+            CUDA_TRY(c, cudaMemcpyAsync(qa, qb, sizeof(double) * (size_t)n * p, cudaMemcpyDeviceToDevice, c->stream));
+        } else {
+            TRY(cholqr(qa, qb, n));
+            CUDA_TRY(c, cudaMemcpyAsync(qa, qb, sizeof(double) * (size_t)n * p, cudaMemcpyDeviceToDevice, c->stream));
+            TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, qa, n, Za, m));            // Z = M Q
+        }
         // Rayleigh-Ritz
-        int splits = 1;
-        TRY(launch_dgemm(c, 0, 0, m, p, n, M, ldm, Qa, n, Za, m));                // Z = M Q
         TRY(launch_dgemm(c, 1, 0, p, p, m, Za, m, Za, m, Gm, p));                 // H = Z^T Z
-        splits = 1;
         // H = L L^T (Cholesky in registers, breakdown -> status -> exact fallback), then Jacobi on the columns of L
-        launch_chol_inv(p, Gm, splits, Ri, Lm, status, c->stream);
+        launch_chol_inv(p, Gm, 1, Ri, Lm, status, c->stream, !c->flag[F_SVD_CHOLSEQ]);
         // register-resident Jacobi (sym_eig_reg.cu) for p = 16k; the shared-memory solver otherwise / on request
         if (c->flag[F_SVD_EIGSMEM] || !launch_sym_eig_reg(p, Lm, Wm, ev, status, c->stream))
             if (launch_sym_eig<true>(p, eig_smem, Lm, 1, p, Wm, ev, status, c->stream)) CUDA_TRY(c, cudaGetLastError());
@@ -686,42 +913,115 @@ restart:
         ritz_trunc_kernel<<<1, 256, 0, c->stream>>>(ev, p, n, trace_dev, chi_max, cutoff, c->perm, ev + p, c->iscal);
         gather_cols_kernel<<<(p * k + 255) / 256, 256, 0, c->stream>>>(Wm, p, c->perm, k, Wk);
         c->launches += 3;
-        TRY(launch_dgemm(c, 0, 0, n, k, p, Qa, n, Wk, p, ortho_core, n));         // V_k = Q W_k
+        TRY(launch_dgemm(c, 0, 0, n, k, p, qa, n, Wk, p, Vs, n));                 // V_k = Q W_k
         TRY(launch_dgemm(c, 0, 0, m, k, p, Za, m, Wk, p, Uk, m));                 // U_k S_k = Z W_k
         // residual of the kept Ritz pairs: M^T (M v_i) - sigma_i^2 v_i
         TRY(launch_dgemm(c, 1, 0, n, k, m, M, ldm, Uk, m, T2, n));
         CUDA_TRY(c, cudaMemsetAsync(resbits, 0, sizeof(unsigned long long), c->stream));
-        residual_kernel<<<k, 256, 0, c->stream>>>(T2, ortho_core, ev + p, c->iscal, n, resbits);
+        residual_kernel<<<k, 256, 0, c->stream>>>(T2, Vs, ev + p, c->iscal, n, resbits);
         c->launches++;
         CUDA_TRY(c, cudaGetLastError());
-        CUDA_TRY(c, cudaMemcpyAsync(c->hiscal, c->iscal, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));   // chi_new, non-finite flag
-        CUDA_TRY(c, cudaMemcpyAsync(c->hiscal + 8, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaMemcpyAsync(c->hscal + 10, resbits, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        // one read-back: chi_new, non-finite flag [0..1], Cholesky / Jacobi status [8..9], residual bits [10..11]
+        CUDA_TRY(c, cudaMemcpyAsync(c->hiscal, c->iscal, 12 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        return MPST_OK;
+    };
+    // graph cache: key = everything the captured sequence depends on (shapes, counts, switches, buffer addresses)
+    auto run_round = [&](bool fresh, int niter, int iters_before) -> int {
+        const bool graphable = !dbg && !c->flag[F_SVD_NOGRAPH] && overlap;
+        if (!graphable) return enqueue_round(fresh, niter, iters_before);
+        // split-K workspaces must not grow inside a capture
+        TRY(ensure_buf(c, &c->gws, &c->gwscap, std::max((size_t)16 * std::max(m, n) * p, (size_t)c->sm_count * p * p)));
+        TRY(ensure_buf(c, &c->gws2, &c->gws2cap, (size_t)c->sm_count * p * p));
+        uint64_t cbits;
+        memcpy(&cbits, &cutoff, sizeof cbits);
+        std::vector<int64_t> key = {m, n, (int64_t)ldm, p, k, niter, fresh ? 1 : 0, chi_max, (int64_t)cbits, C,
+                                    (int64_t)(uintptr_t)M, (int64_t)(uintptr_t)trace_dev, (int64_t)(uintptr_t)c->sub,
+                                    (int64_t)(uintptr_t)c->gws, (int64_t)(uintptr_t)c->gws2, c->flag[F_SVD_CHOLSEQ], c->flag[F_SVD_EIGSMEM]};
+        SvdGraph* g = nullptr;
+        for (auto& e : c->svd_graphs) if (e.key == key) { g = &e; break; }
+        if (!g) {
+            const int64_t l0 = c->launches;
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();
+                c->flag[F_SVD_NOGRAPH] = 1;
+                return enqueue_round(fresh, niter, iters_before);
+            }
+            const int rc = enqueue_round(fresh, niter, iters_before);
+            const cudaError_t ee = cudaStreamEndCapture(c->stream, &graph);
+            const int64_t nl = c->launches - l0;
+            c->launches = l0;
+            cudaGraphExec_t exec = nullptr;
+            if (rc != MPST_OK || ee != cudaSuccess || graph == nullptr || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+                cudaGetLastError();
+                if (graph) cudaGraphDestroy(graph);
+                c->flag[F_SVD_NOGRAPH] = 1;                                        // capture not possible here: plain launches from now on
+                c->err.clear();
+                return enqueue_round(fresh, niter, iters_before);
+            }
+            cudaGraphDestroy(graph);
+            if (c->svd_graphs.size() >= 24) {                                      // drop the least recently used
+                size_t lru = 0;
+                for (size_t i = 1; i < c->svd_graphs.size(); i++) if (c->svd_graphs[i].last_use < c->svd_graphs[lru].last_use) lru = i;
+                cudaGraphExecDestroy((cudaGraphExec_t)c->svd_graphs[lru].exec);
+                c->svd_graphs.erase(c->svd_graphs.begin() + lru);
+            }
+            c->svd_graphs.push_back({key, (void*)exec, nl, 0});
+            g = &c->svd_graphs.back();
+        }
+        g->last_use = ++c->seg_clock;
+        if (c->svd_prepare_only) {
+            // called ahead of the split (while the gradient kernel runs): push the graph's launch state to the device on
+            // the idle side stream, so that the launch itself finds nothing left to do on the host
+            CUDA_TRY(c, cudaGraphUpload((cudaGraphExec_t)g->exec, c->stream2));
+            CUDA_TRY(c, cudaEventRecord(c->ev_upload, c->stream2));
+            c->svd_uploaded = g->exec;
+            return MPST_OK;
+        }
+        if (c->svd_uploaded == g->exec) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_upload, 0));
+        c->svd_uploaded = nullptr;
+        CUDA_TRY(c, cudaGraphLaunch((cudaGraphExec_t)g->exec, c->stream));
+        c->launches += g->launches;
+        return MPST_OK;
+    };
+restart:
+    for (int round = 0; round < max_rounds; round++) {
+        // iterations of the first round: 7 (5 when the subspace has 2k columns) unless this bond's previous visits
+        // showed what reaches the residual bound (trained spectra change slowly from sweep to sweep)
+        const int slot = (c->svd_slot >= 0 && c->svd_slot < (int)c->svd_its.size()) ? c->svd_slot : -1;
+        int first = c->flag[F_SVD_IT] > 0 ? c->flag[F_SVD_IT] : (p >= 2 * k ? 5 : 7);
+        const bool hinted = slot >= 0 && c->svd_its[slot] == 0 && c->flag[F_SVD_IT] <= 0 && c->svd_hint_its > 0 &&
+                            c->svd_hint_m == m && c->svd_hint_n == n;
+        if (slot >= 0 && c->svd_its[slot] > 0 && c->flag[F_SVD_IT] <= 0) first = c->svd_its[slot];
+        else if (hinted) first = std::max(c->svd_hint_its, c->svd_floor[slot]);
+        const int niter = round == 0 ? first : 3;
+        if (c->svd_prepare_only) {
+            if (!dbg && !c->flag[F_SVD_NOGRAPH] && overlap) TRY(run_round(true, niter, 0));
+            return MPST_OK;
+        }
+        TRY(run_round(iters_done == 0, niter, iters_done));
+        iters_done += niter;
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        const double res = c->hscal[10];
+        double res;
+        memcpy(&res, c->hiscal + 10, sizeof(double));
         if (c->hiscal[8] != 0 || !(res == res)) {
-            if (half_orth) {                                                       // retry once without the shortcut
+            if (half_orth || overlap) {                                            // retry once without the shortcuts
                 if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d breakdown with column scaling -> restart with full orth\n", m, n);
-                c->svd_nohalf[slot0] = 1;
+                if (slot0 >= 0) c->svd_nohalf[slot0] = 4;
                 c->last[L_SVD_RESTARTS]++;
                 half_orth = false;
+                overlap = false;
                 iters_done = 0;
-                CUDA_TRY(c, cudaMemsetAsync(status, 0, sizeof(int), c->stream));
-                const int64_t tot = (int64_t)n * p;
-                rand_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(Qa, n, p, n, 0x5DEECE66Dull + (uint64_t)m * 131 + n);
-                c->launches++;
                 goto restart;
             }
             if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d breakdown status=%d -> full Jacobi\n", m, n, c->hiscal[8]);
             return MPST_OK;
         }
-        if (slot >= 0) {
+        if (slot >= 0 && c->flag[F_SVD_PROBE]) {
+            // round-1 policy (kept for comparison): try one iteration fewer whenever the residual passed with a little margin
             if (round == 0 && res <= 5e-14) {
-                // passed at `first`: try one fewer next time if that level has not failed before and the margin is there
                 if (res <= 1.5e-14 && first - 1 >= std::max(3, c->svd_floor[slot])) c->svd_its[slot] = first - 1;
                 else c->svd_its[slot] = first;
-                // ... and the next bond of this shape without history starts one below what just passed with margin,
-                // unless that level already failed somewhere along the chain
                 c->svd_hint_m = m; c->svd_hint_n = n;
                 c->svd_hint_its = (res <= 1.5e-14 && first - 1 >= std::max(3, c->svd_hint_floor)) ? first - 1 : first;
             } else if (round == 0) {
@@ -731,6 +1031,27 @@ restart:
                     c->svd_hint_floor = std::max(c->svd_hint_floor, first + 1);
                     c->svd_hint_its = std::max(c->svd_hint_its, first + 1);
                 }
+            }
+        } else if (slot >= 0) {
+            // An extra iteration costs two products (~80 us at 2048 x 1024), a failed round a whole second Rayleigh-Ritz
+            // (~1 ms): the count is kept where the residual sits at the rounding floor, raised as soon as the margin
+            // to the bound gets thin, and lowered only after the bond has sat at the floor for three visits in a row
+            // (a level that failed on this bond is never tried again).
+            if ((int)c->svd_calm.size() != (int)c->svd_its.size()) c->svd_calm.assign(c->svd_its.size(), 0);
+            if (round == 0 && res <= 5e-14) {
+                int next = first;
+                if (res > 2e-14) { next = std::min(first + 1, 12); c->svd_calm[slot] = 0; }
+                else if (res <= 1.5e-15) {
+                    if (++c->svd_calm[slot] >= 3 && first - 1 >= std::max(3, c->svd_floor[slot])) { next = first - 1; c->svd_calm[slot] = 0; }
+                } else c->svd_calm[slot] = 0;
+                c->svd_its[slot] = next;
+                c->svd_hint_m = m; c->svd_hint_n = n;
+                c->svd_hint_its = std::max(first, next);
+            } else if (round == 0) {
+                c->svd_calm[slot] = 0;
+                c->svd_floor[slot] = first + 1;
+                c->svd_its[slot] = first + 1;
+                if (c->svd_hint_m == m && c->svd_hint_n == n) c->svd_hint_its = std::max(c->svd_hint_its, first + 1);
             }
         }
         if (res <= 5e-14) return finish("subspace", iters_done, res);
