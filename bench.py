@@ -446,7 +446,7 @@ def run_training(m, ctx, w, args, rank, world, local, td, steps, warmup, fp64_pe
     ctx.profile_reset()
     ctx.debug_set("grad_kr_launches", 0)
     ctx.debug_set("grad_tile_launches", 0)
-    SVD_KEYS = ("svd_calls", "svd_iters_sum", "svd_round2", "svd_jacobi", "svd_fast")
+    SVD_KEYS = ("svd_calls", "svd_iters_sum", "svd_round2", "svd_jacobi", "svd_fast", "svd_serial")
     for k in SVD_KEYS:
         ctx.debug_set(k, 0)
     clocks = ClockSampler(local)
@@ -533,7 +533,7 @@ def run_training(m, ctx, w, args, rank, world, local, td, steps, warmup, fp64_pe
         "roofline": roofline, "device_time_breakdown_ms": breakdown, "wall_s_timed": wall,
         "ms_per_bond": ms / (steps * bps),
         "svd_stats": dict(svd_stats, note="timed region: splits, subspace iterations summed over the fast-path splits, splits that "
-                                          "needed a second round of iterations, exact-Jacobi fallbacks, fast-path splits"),
+                                          "needed a second round of iterations, exact-Jacobi fallbacks, fast-path splits, of which in the serial (fully orthonormalising) loop"),
     }
     if e2e is not None:
         out["e2e"] = e2e

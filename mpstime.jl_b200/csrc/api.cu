@@ -222,7 +222,7 @@ const FlagDef kFlags[F_COUNT] = {
 };
 const char* kLast[L_COUNT] = {"svd_path", "svd_iters", "svd_restarts", "grad_kernel", "grad_variant", "krao_kernel",
                               "krao_variant", "fwd_path", "krao_reg_mask", "grad_kr_launches", "grad_tile_launches", "svd_calls",
-                              "svd_iters_sum", "svd_round2", "svd_jacobi", "svd_fast"};
+                              "svd_iters_sum", "svd_round2", "svd_jacobi", "svd_fast", "svd_serial"};
 void flags_from_env(mpst_ctx* c) {
     for (int f = 0; f < F_COUNT; f++) {
         c->flag[f] = kFlags[f].def;
@@ -418,6 +418,7 @@ static int model_reset(mpst_ctx* c, int T, int C, int d, int chi_max) {
     c->svd_floor.clear();
     c->svd_calm.clear();
     c->svd_nohalf.clear();
+    c->svd_pen.clear();
     if ((int)c->cores.size() != T) {
         for (auto& k : c->cores) if (k.dev) cudaFree(k.dev);
         c->cores.assign(T, Core());
@@ -834,7 +835,7 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
                              factored ? &kl : nullptr, factored ? &kr : nullptr, cached));
         if (it == o->update_iters - 1) {
             // the gradient kernel is running and the host has nothing to do: get the CUDA graph of this bond's split ready
-            if ((int)c->svd_its.size() != c->T) { c->svd_its.assign(c->T, 0); c->svd_floor.assign(c->T, 0); c->svd_calm.assign(c->T, 0); c->svd_nohalf.assign(c->T, 0); }
+            if ((int)c->svd_its.size() != c->T) { c->svd_its.assign(c->T, 0); c->svd_floor.assign(c->T, 0); c->svd_calm.assign(c->T, 0); c->svd_nohalf.assign(c->T, 0); c->svd_pen.assign(c->T, 0); }
             c->svd_slot = l;
             const int rcp = svd_split_prepare(c, Dl, Dr, C, going_left, o->chi_max, o->cutoff, o->rescale_after ? s_bn2 : nullptr);
             c->svd_slot = -1;
@@ -870,7 +871,7 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         const size_t cap = (size_t)d * c->chi_max * c->chi_max * C;
         TRY(core_reserve(c, klabel, cap));
         TRY(core_reserve(c, kortho, cap));
-        if ((int)c->svd_its.size() != c->T) { c->svd_its.assign(c->T, 0); c->svd_floor.assign(c->T, 0); c->svd_calm.assign(c->T, 0); c->svd_nohalf.assign(c->T, 0); }
+        if ((int)c->svd_its.size() != c->T) { c->svd_its.assign(c->T, 0); c->svd_floor.assign(c->T, 0); c->svd_calm.assign(c->T, 0); c->svd_nohalf.assign(c->T, 0); c->svd_pen.assign(c->T, 0); }
         c->svd_slot = l;
         const int rc_svd = svd_split_device(c, c->B, Dl, Dr, C, going_left, o->chi_max, o->cutoff, norm2_dev, klabel.dev,
                                             kortho.dev, &chi_new, nullptr, nullptr);

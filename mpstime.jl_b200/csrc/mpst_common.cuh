@@ -66,6 +66,7 @@ enum {
     L_SVD_ROUND2,         // exact Jacobi, fast-path splits (Gram or subspace)
     L_SVD_JACOBI,
     L_SVD_FAST,
+    L_SVD_SERIAL,         // fast-path splits that ran the serial (fully orthonormalising) loop
     L_COUNT
 };
 
@@ -165,7 +166,7 @@ struct mpst_ctx {
     // from its neighbour's count instead of the conservative default (spectra change slowly along the chain)
     int svd_hint_m = 0, svd_hint_n = 0, svd_hint_its = 0, svd_hint_floor = 0;
     std::vector<SvdGraph> svd_graphs;
-    std::vector<char> svd_nohalf;   // bonds on which the column-scaling shortcut of the subspace iteration broke down once
+    std::vector<char> svd_nohalf, svd_pen;   // bonds on which the column-scaling shortcut of the subspace iteration broke down once
     // capacities (doubles) of the training buffers: a re-load with the same or a smaller shape reuses them
     size_t cap_X = 0, cap_PHI = 0, cap_phi = 0, cap_env = 0, cap_ones = 0, cap_yw = 0;
     size_t gwscap = 0;

@@ -58,7 +58,7 @@ __global__ void rand_init_kernel(double* __restrict__ Q, int n, int p, int64_t l
 // (i, j > k) keeps the (full, symmetric) Schur complement, so row k alone carries everything step k needs:
 //     inv = 1/sqrt(m_kk);  l_i = m_ki inv (i > k);  r_j = m_kj inv
 //     m_ij -= l_i r_j (i > k, j != k);  m_ik = -l_i inv (i > k);  m_kj = r_j (j < k);  m_kk = inv.
-// status[0] |= 1 when a pivot is not safely positive (caller falls back to the exact SVD).
+// status[0] |= 1 on NaN input (caller falls back to the exact SVD); numerically dependent columns are deflated (below).
 template <int NRR, int NRC, int TYN>
 __global__ void __launch_bounds__(TYN * 16)
 chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restrict__ Rinv, double* __restrict__ Lout,
@@ -108,9 +108,13 @@ chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restr
             if (ty + TYN * r == tx + 16 * cc && ty + TYN * r < p) s_diag[ty + TYN * r] = m[r][cc];
     __syncthreads();
     // A pivot is the squared norm of column k of the factored matrix after projecting out columns < k; relative to
-    // the column's own squared norm g_kk it is sin^2 of the angle to their span.  Below ~1e-13 CholeskyQR is no
-    // longer trustworthy.  The test is per column (Cholesky itself is invariant under column scaling), so graded
-    // columns -- norms spread over orders of magnitude but directions well separated -- pass.
+    // the column's own squared norm g_kk it is sin^2 of the angle to their span.  The test is per column (Cholesky
+    // itself is invariant under column scaling), so graded columns -- norms spread over orders of magnitude but
+    // directions well separated -- pass.  A column below 1e-13 is numerically inside the span of its predecessors
+    // (the tail of a bond tensor below rounding level, or a rank-deficient bond early in training): it is DEFLATED --
+    // 1/l_kk := 0 makes row and column k of both L and L^-1 zero, so X R^-1 simply has a zero column there and every
+    // other column is what it would be without column k.  A zero column stays zero through M, M^T, the second pass and
+    // the Rayleigh-Ritz step (Ritz value 0, ranked last).  status bit 0 is left for NaN input.
     bool bad = false;
 #ifdef MPST_KDEBUG
     const long long tk0 = clock64();
@@ -136,8 +140,8 @@ chol_inv_kernel(const double* __restrict__ G, int splits, int p, double* __restr
                 __syncthreads();                       // the only barrier of the step (row buffers alternate)
                 const double dk = rk[k];
                 const double tiny = 1e-13 * s_diag[k];
-                bad |= !(dk > tiny);
-                const double inv = rsqrt(dk > tiny ? dk : fmax(tiny, 1e-300));      // 1 / l_kk
+                bad |= !(dk == dk);
+                const double inv = dk > tiny ? rsqrt(dk) : 0.0;       // 1 / l_kk, or 0: column k is deflated
                 double li[NRR], rj[NRC];
 #pragma unroll
                 for (int r = krr; r < NRR; r++) {
@@ -235,8 +239,8 @@ chol_inv_blk_kernel(const double* __restrict__ G, double* __restrict__ Rinv, dou
             for (int k = 0; k < 8; k++) {
                 const double dk = a[k][k];
                 const double tiny = 1e-13 * s_diag[k0 + k];
-                bad |= !(dk > tiny);
-                inv[k] = rsqrt(dk > tiny ? dk : fmax(tiny, 1e-300));
+                bad |= !(dk == dk);
+                inv[k] = dk > tiny ? rsqrt(dk) : 0.0;             // 0: column deflated (see chol_inv_kernel)
                 a[k][k] = dk * inv[k];
 #pragma unroll
                 for (int i = k + 1; i < 8; i++) a[i][k] *= inv[k];
@@ -1007,7 +1011,13 @@ restart:
         if (c->hiscal[8] != 0 || !(res == res)) {
             if (half_orth || overlap) {                                            // retry once without the shortcuts
                 if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d breakdown with column scaling -> restart with full orth\n", m, n);
-                if (slot0 >= 0) c->svd_nohalf[slot0] = 4;
+                if (slot0 >= 0) {
+                    // back-off: 1, 2, 4, 8 visits down the serial loop for a bond that keeps breaking down (a genuinely
+                    // rank-deficient bond); a rank-deficient first sweep (chi_init start) costs the next visit only
+                    if ((int)c->svd_pen.size() != (int)c->svd_nohalf.size()) c->svd_pen.assign(c->svd_nohalf.size(), 0);
+                    c->svd_pen[slot0] = (char)std::min(8, std::max(1, 2 * (int)c->svd_pen[slot0]));
+                    c->svd_nohalf[slot0] = (char)(c->svd_pen[slot0] + 1);
+                }
                 c->last[L_SVD_RESTARTS]++;
                 half_orth = false;
                 overlap = false;
@@ -1054,7 +1064,11 @@ restart:
                 if (c->svd_hint_m == m && c->svd_hint_n == n) c->svd_hint_its = std::max(c->svd_hint_its, first + 1);
             }
         }
-        if (res <= 5e-14) return finish("subspace", iters_done, res);
+        if (res <= 5e-14) {
+            if (overlap && slot0 >= 0 && (int)c->svd_pen.size() == (int)c->svd_nohalf.size()) c->svd_pen[slot0] = 0;
+            if (!overlap) c->last[L_SVD_SERIAL]++;
+            return finish("subspace", iters_done, res);
+        }
         if (round == 0) c->last[L_SVD_ROUND2]++;
         if (res > (round == 0 ? 1e-5 : 1e-10)) {                                   // spectrum too flat: full Jacobi
             if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d residual %.2e after %d its -> full Jacobi\n", m, n, res, iters_done);

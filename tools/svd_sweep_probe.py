@@ -24,11 +24,11 @@ for st in SETTINGS:
     ctx.train_load_x(Xs, counts, d, chi)
     ctx.set_cores(cores0)
     ctx.sweep_bonds(topts, 2 * (T - 1), restart=True, record=False)          # first sweep: chi grows, flat spectra
-    for k in ("svd_calls", "svd_iters_sum", "svd_round2", "svd_jacobi", "svd_fast"):
+    for k in ("svd_calls", "svd_iters_sum", "svd_round2", "svd_jacobi", "svd_fast", "svd_serial"):
         ctx.debug_set(k, 0)
     ctx.profile_enable(True); ctx.profile_reset()
     lo, gn, ch = ctx.sweep_bonds(topts, ns * 2 * (T - 1))
     pr = ctx.profile_get(); ctx.profile_enable(False)
-    g = {k: ctx.debug_get(k) for k in ("svd_calls", "svd_iters_sum", "svd_round2", "svd_jacobi", "svd_fast")}
+    g = {k: ctx.debug_get(k) for k in ("svd_calls", "svd_iters_sum", "svd_round2", "svd_jacobi", "svd_fast", "svd_serial")}
     print(f"{str(st):24s} svd {pr['svd'][0] / pr['svd'][1]:.3f} ms/split  iters/fast-split {g['svd_iters_sum'] / max(g['svd_fast'], 1):.2f}  "
-          f"round2 {g['svd_round2']}  jacobi {g['svd_jacobi']}  of {g['svd_calls']}  final loss {lo[-1]:.6f} mean chi {ch.mean():.1f}", flush=True)
+          f"round2 {g['svd_round2']}  jacobi {g['svd_jacobi']} serial {g['svd_serial']}  of {g['svd_calls']}  final loss {lo[-1]:.6f} mean chi {ch.mean():.1f}", flush=True)
