@@ -14,6 +14,9 @@
 #include "mpst_common.cuh"
 #include "dmma.cuh"
 
+int launch_krao_slab(mpst_ctx* c, const double* x, const double* E, const double* W, double* out, int64_t row_begin,
+                     int64_t row_end, int d, int chi, int n_out, int64_t ldw, int64_t ldo, bool* handled);
+
 namespace {
 constexpr int KC = 16, LDP = KC + 4;
 
@@ -278,6 +281,11 @@ int launch_krao_gemm_rows(mpst_ctx* c, const double* x, const double* E, const d
     const size_t big = 16 + sizeof(double) * ((size_t)128 * chi + (size_t)128 * d + 2 * 128 * LDP +
                                               2 * (n_out > 64 ? 128 : 64) * LDP);
 #define ARGS c, x, E, W, out, row_begin, row_end, d, chi, n_out, ldw, ldo
+    {   // wide outputs: W streamed in K-slabs through the register-operand scheme (krao_slab.cu)
+        bool handled = false;
+        TRY(launch_krao_slab(ARGS, &handled));
+        if (handled) return MPST_OK;
+    }
     // narrow outputs with W resident in shared memory: the register-operand kernel (needs 16-byte columns, d >= 4)
     if (n_out <= 48 && n_out >= 8 && d >= 4 && ((d * chi) % 4) == 0 && (ldw % 2) == 0 && row_end - row_begin >= 256 &&
         !c->flag[F_KRAO_NOREG]) {

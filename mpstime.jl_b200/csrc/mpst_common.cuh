@@ -45,7 +45,7 @@ struct Timer {
 enum {
     F_DENSE_FWD = 0, F_NO_ENV_REUSE, F_GRAD_T128, F_GRAD_NOKR, F_IMPUTE_NODBUF, F_IMPUTE_DEBUG, F_KRAO_NOREG,
     F_SVD_INNER, F_SVD_DEBUG, F_SVD_SKIP, F_SVD_FIXED, F_SVD_FULL, F_SVD_PB64, F_SVD_LEGACY, F_SVD_NOSUB, F_SVD_OVS,
-    F_SVD_NOHALF, F_SVD_HALF_FROM, F_SVD_IT, F_SVD_NOGRAPH, F_GRAD_KC, F_IMPUTE_NOSERIES, F_IMPUTE_FULLSYM, F_GRAD_PHASES, F_SVD_EIGSMEM, F_SVD_SERIAL, F_SVD_CHOLSEQ, F_SVD_PROBE, F_SVD_SYNCFIRST, F_SVD_NOPREP, F_COUNT
+    F_SVD_NOHALF, F_SVD_HALF_FROM, F_SVD_IT, F_SVD_NOGRAPH, F_GRAD_KC, F_IMPUTE_NOSERIES, F_IMPUTE_FULLSYM, F_GRAD_PHASES, F_SVD_EIGSMEM, F_SVD_SERIAL, F_SVD_CHOLSEQ, F_SVD_PROBE, F_SVD_SYNCFIRST, F_SVD_NOPREP, F_KRAO_NOSLAB, F_KRAO_SLAB_MI, F_COUNT
 };
 // which code path the last call took (mpst_debug_get): lets the parity tests assert that they exercised the
 // kernels the benchmark runs, and lets bench.py name the kernel it reports a roofline for
@@ -67,6 +67,7 @@ enum {
     L_SVD_JACOBI,
     L_SVD_FAST,
     L_SVD_SERIAL,         // fast-path splits that ran the serial (fully orthonormalising) loop
+    L_KRAO_SLAB_LAUNCHES, // launches of krao_slab_kernel since last cleared
     L_COUNT
 };
 
@@ -145,6 +146,8 @@ struct mpst_ctx {
     double* sub = nullptr;      // subspace-SVD workspace
     size_t subcap = 0;
     double* gws = nullptr;      // split-K partial products of the small GEMMs
+    double* kslab = nullptr;    // K6: slab-major copy of the weight matrix (krao_slab.cu)
+    size_t kslabcap = 0;
     double* gws2 = nullptr;     // ... of the GEMMs on the side stream
     size_t gws2cap = 0;
     cudaStream_t stream2 = nullptr;            // side stream of the subspace SVD (Gram + Cholesky next to the big product)

@@ -12,7 +12,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SVD_SUBSPACE, GRAD_KR, GRAD_TILES, KRAO_REG, KRAO_TILES = 3, 1, 2, 1, 2
+SVD_SUBSPACE, GRAD_KR, GRAD_TILES, KRAO_REG, KRAO_TILES, KRAO_SLAB = 3, 1, 2, 1, 2, 3
 
 
 def _device_trained(ctx, oracle, pkg, N, T, d, chi_max, nsweeps, eta=0.05, seed=1):
@@ -80,7 +80,7 @@ def test_teacher_forced_bonds_at_benchmark_shapes(ctx, oracle, pkg, N, T, d, chi
         if chi <= 48:
             assert (kk, kv) == (KRAO_REG, (chi + 7) // 8)
         else:
-            assert kk == KRAO_TILES
+            assert kk == KRAO_SLAB
     assert seen_subspace == len(bonds)
 
 
@@ -153,6 +153,34 @@ def test_subspace_svd_cutoff_decided_truncation(ctx, oracle, d, chi, C, knee, r1
     # the cutoff is a RELATIVE tail weight: the same matrix scaled by 7 splits identically (sigma scales, chi does not)
     _, _, sig7 = ctx.bond_split(7.0 * B, d, chi, chi, True, chimax)
     assert len(sig7) == len(rs) and np.abs(sig7 - 7.0 * rs).max() < 1e-9 * rs.max()
+
+
+@pytest.mark.parametrize("d,chi", [(16, 64), (12, 64), (8, 52), (16, 128)])
+def test_krao_slab_kernel(ctx, oracle, d, chi):
+    """K6/K7 for wide outputs: krao_slab_kernel (W streamed in K-slabs, register operands) vs the oracle and vs the
+    shared-memory tile kernel it replaces (MPST_KRAO_NOSLAB), both row-block sizes."""
+    N, T, C = 1500, 4, 2
+    rng = np.random.default_rng(d * chi)
+    X = rng.uniform(-1, 1, (T, N))
+    phi = oracle.encode(X.T, d)
+    cores = oracle.random_start_mps(T, d, chi, C, seed=chi)
+    ctx.model_init(T, C, d, chi)
+    ctx.set_cores(cores)
+    ref = oracle.overlaps(cores, phi)
+    outs = {}
+    for name, flags in (("slab4", {"KRAO_NOSLAB": 0, "KRAO_SLAB_MI": 4}), ("slab2", {"KRAO_NOSLAB": 0, "KRAO_SLAB_MI": 2}),
+                        ("tiles", {"KRAO_NOSLAB": 1, "KRAO_SLAB_MI": 0})):
+        for k, v in flags.items():
+            ctx.debug_set(k, v)
+        ctx.debug_set("krao_slab_launches", 0)
+        yh, am = ctx.overlaps(X_TxN=X)
+        outs[name] = (yh, ctx.debug_get("krao_slab_launches"))
+        assert np.abs(yh - ref).max() < 1e-12 * np.abs(ref).max(), name
+        assert np.array_equal(am, np.argmax(ref * ref, axis=1)), name
+    ctx.debug_set("KRAO_NOSLAB", 0)
+    ctx.debug_set("KRAO_SLAB_MI", 0)
+    assert outs["slab4"][1] > 0 and outs["slab2"][1] > 0 and outs["tiles"][1] == 0
+    assert np.abs(outs["slab4"][0] - outs["tiles"][0]).max() < 1e-12 * np.abs(ref).max()
 
 
 @pytest.mark.parametrize("chi", [17, 24, 32, 40, 48])
