@@ -50,8 +50,8 @@ struct ImpParams {
     int max_trials;                 // ITS with rejection: draws per site
     double rej_thr;                 // ITS: accept when |x - median| < rej_thr * WMAD; < 0 = :none
     int64_t ustride;                // rejection mode: uniforms per instance (flat stream, consumed in order)
-    // Legendre-series pdf: nq = 2d-1 Gauss-Legendre nodes; leg_pq[l][i] = P_l(node_i) (d x nq), leg_wq[k][i] =
-    // (2k+1)/2 w_i P_k(node_i) (nq x nq); null = direct evaluation
+    // series pdf: nq = 2d-1 Chebyshev-Gauss nodes; leg_pq[l][i] = P_l(node_i) (d x nq), leg_wq[k][i] =
+    // (k == 0 ? 1 : 2) / nq T_k(node_i) (nq x nq, the Chebyshev analysis matrix); null = direct evaluation
     const double* leg_pq;
     const double* leg_wq;
     int nq;
@@ -185,33 +185,31 @@ __device__ __forceinline__ void pdf_legendre(const double* __restrict__ Rt, cons
     }
 }
 
-// Clenshaw coefficients of the Legendre recurrence: b_k = q_k + a_k x b_{k+1} - c_k b_{k+2}
-__constant__ double c_cl_a[2 * MPST_MAX_D];
-__constant__ double c_cl_c[2 * MPST_MAX_D];
-
-// p[g] = sum_k q_k P_k(x_g): the pdf || rho Phi(x) ||^2 of a Legendre basis of dimension d is a polynomial of degree
-// 2(d-1) in x, so after an exact change to its own Legendre series (2d-1 coefficients, see the caller) a grid point
-// costs 3(2d-1) flops-instructions instead of ~d^2 + 2d.  NP points per thread at a time for ILP.
+// p[g] = sum_k q_k T_k(x_g): the pdf || rho Phi(x) ||^2 of a Legendre basis of dimension d is a polynomial of degree
+// 2(d-1) in x, so after an exact change to its own CHEBYSHEV series (2d-1 coefficients, see the caller) a grid point
+// costs 2(2d-1) flop-instructions (Clenshaw: b_k = q_k + 2x b_{k+1} - b_{k+2}, one add and one FMA per term; the
+// Legendre recurrence needs three) instead of ~d^2 + 2d.  NP points per thread at a time for ILP.
 template <int NP>
 __device__ __forceinline__ void pdf_legendre_series(const double* __restrict__ q, int nq, const double* __restrict__ grid,
                                                     int g0, int g1, double* __restrict__ pbuf) {
     for (int g = g0; g < g1; g += NP) {
-        double x[NP], b1[NP], b2[NP];
+        double x[NP], y[NP], b1[NP], b2[NP];
 #pragma unroll
-        for (int u = 0; u < NP; u++) { x[u] = grid[min(g + u, g1 - 1)]; b1[u] = 0.0; b2[u] = 0.0; }
+        for (int u = 0; u < NP; u++) { x[u] = grid[min(g + u, g1 - 1)]; y[u] = 2.0 * x[u]; b1[u] = 0.0; b2[u] = 0.0; }
 #pragma unroll 1
-        for (int k = nq - 1; k >= 0; k--) {
-            const double a = c_cl_a[k], cc = c_cl_c[k], qk = q[k];
+        for (int k = nq - 1; k >= 1; k--) {
+            const double qk = q[k];
 #pragma unroll
             for (int u = 0; u < NP; u++) {
-                const double t = fma(a * x[u], b1[u], fma(-cc, b2[u], qk));
+                const double t = fma(y[u], b1[u], qk - b2[u]);
                 b2[u] = b1[u];
                 b1[u] = t;
             }
         }
+        const double q0 = q[0];
 #pragma unroll
         for (int u = 0; u < NP; u++)
-            if (g + u < g1) pbuf[g + u] = fmax(b1[u], 0.0);
+            if (g + u < g1) pbuf[g + u] = fmax(fma(x[u], b1[u], q0 - b2[u]), 0.0);
     }
 }
 
@@ -280,11 +278,12 @@ __device__ __forceinline__ void stage_slice_async(double* __restrict__ As, const
                                                   int ld) {
     const double* src = A + (size_t)s * cl * cr;
     const int half = cr >> 1;                          // 16-byte chunks per row
-    for (int e = threadIdx.x; e < cl * half; e += NT) {
-        const int a = e / half, b2 = e - a * half;
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(As + a * ld + 2 * b2);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)a * cr + 2 * b2) : "memory");
-    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int a = warp; a < cl; a += NT / 32)           // a row per warp at a time: no index division
+        for (int b2 = lane; b2 < half; b2 += 32) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(As + a * ld + 2 * b2);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)a * cr + 2 * b2) : "memory");
+        }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void stage_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -543,9 +542,9 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                         }
                         __syncthreads();
                         if (P.leg_pq != nullptr) {
-                            // exact Legendre series of the degree-2(d-1) polynomial p: sample it at the nq = 2d-1 Gauss
-                            // nodes (d^2 flops each, nq points instead of G), discrete Legendre transform (the quadrature
-                            // is exact for degree <= 4d-3), then Clenshaw on the grid
+                            // exact Chebyshev series of the degree-2(d-1) polynomial p: sample it at the nq = 2d-1
+                            // Chebyshev-Gauss nodes (d^2 flops each, nq points instead of G), discrete cosine transform
+                            // (exact for degree <= nq - 1), then Clenshaw on the grid
                             const int nq = P.nq;
                             for (int i = tid; i < nq; i += NT) {
                                 double pv = 0.0;
@@ -912,47 +911,27 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     }
     P.leg_pq = nullptr; P.leg_wq = nullptr; P.nq = 0;
     if ((c->basis == MPST_BASIS_LEGENDRE_NO_NORM || c->basis == MPST_BASIS_LEGENDRE_NORM) && d >= 8 && !c->flag[F_IMPUTE_NOSERIES]) {
-        // Gauss-Legendre rule with nq = 2d-1 nodes (Newton on P_nq), P_l at the nodes and the analysis matrix
+        // Chebyshev-Gauss nodes x_i = cos(pi (i + 1/2) / nq), nq = 2d-1; P_l at the nodes and the analysis matrix
+        // wq[k][i] = (k == 0 ? 1 : 2) / nq * T_k(x_i) (discrete orthogonality: exact for polynomials of degree < nq)
         const int nq = 2 * d - 1;
-        std::vector<double> xs(nq), ws(nq), tab((size_t)d * nq + (size_t)nq * nq);
+        std::vector<double> xs(nq), tab((size_t)d * nq + (size_t)nq * nq);
         const double pi = 3.14159265358979323846;
-        for (int i = 0; i < nq; i++) {
-            double x = cos(pi * (i + 0.75) / (nq + 0.5)), dp = 1.0;
-            for (int it = 0; it < 100; it++) {
-                double p0 = 1.0, p1 = x;
-                for (int l = 2; l <= nq; l++) { const double pn = ((2 * l - 1) * x * p1 - (l - 1) * p0) / l; p0 = p1; p1 = pn; }
-                dp = nq * (x * p1 - p0) / (x * x - 1.0);
-                const double dx = p1 / dp;
-                x -= dx;
-                if (fabs(dx) < 1e-16) break;
-            }
-            {   // derivative at the converged node
-                double p0 = 1.0, p1 = x;
-                for (int l = 2; l <= nq; l++) { const double pn = ((2 * l - 1) * x * p1 - (l - 1) * p0) / l; p0 = p1; p1 = pn; }
-                dp = nq * (x * p1 - p0) / (x * x - 1.0);
-            }
-            xs[i] = x;
-            ws[i] = 2.0 / ((1.0 - x * x) * dp * dp);
-        }
+        for (int i = 0; i < nq; i++) xs[i] = cos(pi * (i + 0.5) / nq);
         double* pq = tab.data();
         double* wq = tab.data() + (size_t)d * nq;
         for (int i = 0; i < nq; i++) {
             double p0 = 1.0, p1 = xs[i];
-            for (int l = 0; l < nq; l++) {
+            for (int l = 0; l < d; l++) {
                 const double pl = l == 0 ? 1.0 : l == 1 ? xs[i] : ((2 * l - 1) * xs[i] * p1 - (l - 1) * p0) / l;
                 if (l >= 2) { p0 = p1; p1 = pl; }
-                if (l < d) pq[(size_t)l * nq + i] = pl;
-                wq[(size_t)l * nq + i] = 0.5 * (2 * l + 1) * ws[i] * pl;
+                pq[(size_t)l * nq + i] = pl;
             }
+            for (int k = 0; k < nq; k++) wq[(size_t)k * nq + i] = (k == 0 ? 1.0 : 2.0) / nq * cos(pi * k * (i + 0.5) / nq);
         }
         double* dtab = nullptr;
         IMP_TRY(reserve(12, sizeof(double) * tab.size(), (void**)&dtab));
         IMP_TRY(cudaMemcpyAsync(dtab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, c->stream));
-        double ca[2 * MPST_MAX_D], cc2[2 * MPST_MAX_D];
-        for (int k = 0; k < 2 * MPST_MAX_D; k++) { ca[k] = (double)(2 * k + 1) / (double)(k + 1); cc2[k] = (double)(k + 1) / (double)(k + 2); }
-        IMP_TRY(cudaMemcpyToSymbolAsync(c_cl_a, ca, sizeof(ca), 0, cudaMemcpyHostToDevice, c->stream));
-        IMP_TRY(cudaMemcpyToSymbolAsync(c_cl_c, cc2, sizeof(cc2), 0, cudaMemcpyHostToDevice, c->stream));
-        IMP_TRY(cudaStreamSynchronize(c->stream));                 // tab / ca / cc2 are stack / local temporaries
+        IMP_TRY(cudaStreamSynchronize(c->stream));                 // tab is a local temporary
         P.leg_pq = dtab; P.leg_wq = dtab + (size_t)d * nq; P.nq = nq;
     }
     IMP_TRY(cudaFuncSetAttribute(impute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

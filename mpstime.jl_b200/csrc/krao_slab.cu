@@ -17,11 +17,10 @@
 #include "dmma.cuh"
 
 namespace {
-constexpr int NCOL = 64;                               // output columns per block (8 fragments)
 
 // W2[cb][slab][n][kk] = W[(cb*64 + n) * ldw + slab*KS + kk]   (zero for n >= n_out), pitch KS + 4
 __global__ void pack_w_slabs_kernel(const double* __restrict__ W, int64_t ldw, int n_out, int K, int KS, int nslab,
-                                    double* __restrict__ W2) {
+                                    int NCOL, double* __restrict__ W2) {
     const int pitch = KS + 4;
     const int64_t tot = (int64_t)gridDim.y * nslab * NCOL * pitch;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)nslab * NCOL * pitch;
@@ -35,11 +34,12 @@ __global__ void pack_w_slabs_kernel(const double* __restrict__ W, int64_t ldw, i
     }
 }
 
-template <int MI, int DQ, int ST, int OCC>
+template <int MI, int DQ, int NI, int ST, int OCC>
 __global__ void __launch_bounds__(256, OCC)
 krao_slab_kernel(const double* __restrict__ x, const double* __restrict__ E, const double* __restrict__ W2,
                  double* __restrict__ out, int64_t row_begin, int64_t row_end, int d, int chi, int n_out, int64_t ldo,
                  int nslab) {
+    constexpr int NCOL = 8 * NI;                                           // output columns per block
     constexpr int KS = 16 * DQ, PITCH = KS + 4, SLAB = NCOL * PITCH;      // doubles per slab
     constexpr int ROWS = 8 * MI;                                           // samples per warp
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -91,11 +91,11 @@ krao_slab_kernel(const double* __restrict__ x, const double* __restrict__ E, con
 #pragma unroll
             for (int q = 0; q < DQ; q++) xq[mi][q] = x[i * d + 4 * q + fc];
         }
-        double acc[MI][8][2];
+        double acc[MI][NI][2];
 #pragma unroll
         for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-            for (int ni = 0; ni < 8; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
         double en[MI];                                                     // E_i[a + 1], in flight while link value a is consumed
 #pragma unroll
         for (int mi = 0; mi < MI; mi++) en[mi] = er[mi][0];
@@ -113,15 +113,15 @@ krao_slab_kernel(const double* __restrict__ x, const double* __restrict__ E, con
 #pragma unroll
                 for (int q = 0; q < DQ; q++) {
                     const int kk = 4 * (j * DQ + q);                       // k-step inside the slab: k = s + d a, s = 4 q + fc
-                    double a[MI], b[8];
+                    double a[MI], b[NI];
 #pragma unroll
                     for (int mi = 0; mi < MI; mi++) a[mi] = xq[mi][q] * ec[mi];
 #pragma unroll
-                    for (int ni = 0; ni < 8; ni++) b[ni] = wp[(size_t)ni * 8 * PITCH + kk];
+                    for (int ni = 0; ni < NI; ni++) b[ni] = wp[(size_t)ni * 8 * PITCH + kk];
 #pragma unroll
                     for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-                        for (int ni = 0; ni < 8; ni++) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                        for (int ni = 0; ni < NI; ni++) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
                 }
             }
             __syncwarp();
@@ -132,7 +132,7 @@ krao_slab_kernel(const double* __restrict__ x, const double* __restrict__ E, con
             const int64_t i = i0 + mi * 8 + fr;
             if (i < row_begin || i >= row_end) continue;
 #pragma unroll
-            for (int ni = 0; ni < 8; ni++) {
+            for (int ni = 0; ni < NI; ni++) {
                 const int n = col0 + ni * 8 + 2 * fc;
                 if (n < n_out) out[i * ldo + n] = acc[mi][ni][0];
                 if (n + 1 < n_out) out[i * ldo + n + 1] = acc[mi][ni][1];
@@ -141,12 +141,12 @@ krao_slab_kernel(const double* __restrict__ x, const double* __restrict__ E, con
     }
 }
 
-template <int MI, int DQ, int ST, int OCC>
+template <int MI, int DQ, int NI, int ST, int OCC>
 int launch_slab_t(mpst_ctx* c, const double* x, const double* E, const double* W2, double* out, int64_t row_begin,
                   int64_t row_end, int d, int chi, int n_out, int64_t ldo, int nslab, int ncb) {
     constexpr int KS = 16 * DQ;
-    const size_t smem = 128 + sizeof(double) * (size_t)ST * NCOL * (KS + 4);
-    auto kern = krao_slab_kernel<MI, DQ, ST, OCC>;
+    const size_t smem = 128 + sizeof(double) * (size_t)ST * 8 * NI * (KS + 4);
+    auto kern = krao_slab_kernel<MI, DQ, NI, ST, OCC>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntile = (row_end + 64 * MI - 1) / (64 * MI) - row_begin / (64 * MI);
     const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(OCC * c->sm_count / ncb, ntile));
@@ -155,39 +155,63 @@ int launch_slab_t(mpst_ctx* c, const double* x, const double* E, const double* W
     CUDA_TRY(c, cudaGetLastError());
     c->last[L_KRAO_KERNEL] = 3;
     c->last[L_KRAO_SLAB_LAUNCHES]++;
-    c->last[L_KRAO_VARIANT] = 10 * MI + DQ;
+    c->last[L_KRAO_VARIANT] = 100 * NI + 10 * MI + DQ;
     return MPST_OK;
+}
+
+template <int DQ, int NI>
+int launch_slab_mi(mpst_ctx* c, int mi, const double* x, const double* E, const double* W2, double* out, int64_t row_begin,
+                   int64_t row_end, int d, int chi, int n_out, int64_t ldo, int nslab, int ncb) {
+#define SLAB_ARGS c, x, E, W2, out, row_begin, row_end, d, chi, n_out, ldo, nslab, ncb
+    if constexpr (NI == 8) {
+        if (mi == 4) return launch_slab_t<4, DQ, NI, 4, 1>(SLAB_ARGS);
+        if (mi == 22) return launch_slab_t<2, DQ, NI, 3, 2>(SLAB_ARGS);     // two CTAs per SM: 3-stage ring, 128 registers
+    }
+    if constexpr (NI <= 4) return launch_slab_t<4, DQ, NI, 4, 1>(SLAB_ARGS); // narrow blocks: 32 samples per warp
+    return launch_slab_t<2, DQ, NI, 4, 1>(SLAB_ARGS);
+#undef SLAB_ARGS
+}
+
+template <int DQ>
+int launch_slab_ni(mpst_ctx* c, int ni, int mi, const double* x, const double* E, const double* W2, double* out,
+                   int64_t row_begin, int64_t row_end, int d, int chi, int n_out, int64_t ldo, int nslab, int ncb) {
+#define SLAB_ARGS c, mi, x, E, W2, out, row_begin, row_end, d, chi, n_out, ldo, nslab, ncb
+    switch (ni) {
+        case 4: return launch_slab_mi<DQ, 4>(SLAB_ARGS);
+        case 5: return launch_slab_mi<DQ, 5>(SLAB_ARGS);
+        case 6: return launch_slab_mi<DQ, 6>(SLAB_ARGS);
+        case 7: return launch_slab_mi<DQ, 7>(SLAB_ARGS);
+        default: return launch_slab_mi<DQ, 8>(SLAB_ARGS);
+    }
+#undef SLAB_ARGS
 }
 }  // namespace
 
-// *handled = false: shape not covered (caller uses krao_gemm_kernel).  Covered: d in {8, 12, 16}, chi % 4 == 0,
-// n_out > 48, at least two tiles of rows.
+// *handled = false: shape not covered (caller uses krao_reg_kernel / krao_gemm_kernel).  Covered: d in {8, 12, 16, 24},
+// chi % 4 == 0, more than 24 output columns (split into equal blocks of at most 64), at least two tiles of rows.
 int launch_krao_slab(mpst_ctx* c, const double* x, const double* E, const double* W, double* out, int64_t row_begin,
                      int64_t row_end, int d, int chi, int n_out, int64_t ldw, int64_t ldo, bool* handled) {
     *handled = false;
-    if (c->flag[F_KRAO_NOSLAB] || (d != 8 && d != 12 && d != 16) || (chi & 3) || n_out <= 48 || row_end - row_begin < 512)
+    if (c->flag[F_KRAO_NOSLAB] || (d != 8 && d != 12 && d != 16 && d != 24) || (chi & 3) || n_out <= 24 ||
+        n_out < c->flag[F_KRAO_SLAB_MIN] || row_end - row_begin < 512)
         return MPST_OK;
-    const int DQ = d / 4, KS = 16 * DQ, nslab = chi / 4, ncb = (n_out + NCOL - 1) / NCOL;
-    const size_t need = (size_t)ncb * nslab * NCOL * (KS + 4);
+    const int DQ = d / 4, KS = 16 * DQ, nslab = chi / 4;
+    const int ncb = (n_out + 63) / 64;
+    const int ni = (((n_out + ncb - 1) / ncb) + 7) / 8;                     // fragments per column block, 4..8
+    const int ncol = 8 * std::max(ni, 4);
+    const size_t need = (size_t)ncb * nslab * ncol * (KS + 4);
     TRY(ensure_buf(c, &c->kslab, &c->kslabcap, need));
-    pack_w_slabs_kernel<<<dim3(32, ncb), 256, 0, c->stream>>>(W, ldw, n_out, d * chi, KS, nslab, c->kslab);
+    pack_w_slabs_kernel<<<dim3(32, ncb), 256, 0, c->stream>>>(W, ldw, n_out, d * chi, KS, nslab, ncol, c->kslab);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
     *handled = true;
-    const int mi = c->flag[F_KRAO_SLAB_MI] > 0 ? c->flag[F_KRAO_SLAB_MI] : 2;
-#define SLAB_ARGS c, x, E, c->kslab, out, row_begin, row_end, d, chi, n_out, ldo, nslab, ncb
-    if (mi == 4) {
-        if (DQ == 4) return launch_slab_t<4, 4, 4, 1>(SLAB_ARGS);
-        if (DQ == 3) return launch_slab_t<4, 3, 4, 1>(SLAB_ARGS);
-        return launch_slab_t<4, 2, 4, 1>(SLAB_ARGS);
+    const int mi = c->flag[F_KRAO_SLAB_MI];
+#define SLAB_ARGS c, std::max(ni, 4), mi, x, E, c->kslab, out, row_begin, row_end, d, chi, n_out, ldo, nslab, ncb
+    switch (DQ) {
+        case 2: return launch_slab_ni<2>(SLAB_ARGS);
+        case 3: return launch_slab_ni<3>(SLAB_ARGS);
+        case 4: return launch_slab_ni<4>(SLAB_ARGS);
+        default: return launch_slab_ni<6>(SLAB_ARGS);
     }
-    if (mi == 22) {                                    // two CTAs per SM: 3-stage ring, 128 registers
-        if (DQ == 4) return launch_slab_t<2, 4, 3, 2>(SLAB_ARGS);
-        if (DQ == 3) return launch_slab_t<2, 3, 3, 2>(SLAB_ARGS);
-        return launch_slab_t<2, 2, 3, 2>(SLAB_ARGS);
-    }
-    if (DQ == 4) return launch_slab_t<2, 4, 4, 1>(SLAB_ARGS);
-    if (DQ == 3) return launch_slab_t<2, 3, 4, 1>(SLAB_ARGS);
-    return launch_slab_t<2, 2, 4, 1>(SLAB_ARGS);
 #undef SLAB_ARGS
 }

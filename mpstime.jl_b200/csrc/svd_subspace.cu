@@ -463,7 +463,7 @@ sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* _
                 double ga = 0.0;
 #pragma unroll
                 for (int t = 0; t < NT; t++) {
-                    const bool in = FULL || (l16 + 16 * t < p);
+                    const bool in = active && (FULL || (l16 + 16 * t < p));   // a half-warp without a pair reads nothing
                     xa[t] = in ? ha[16 * t] : 0.0;
                     xb[t] = in ? hb[16 * t] : 0.0;
                     ga = fma(xa[t], xb[t], ga);
@@ -506,8 +506,8 @@ sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* _
                         const double cs2 = 2.0 * c * sn * ga, cc = c * c, ss = sn * sn;
                         nrm[ca] = cc * al - cs2 + ss * be;
                         nrm[cb] = ss * al + cs2 + cc * be;
-                        any_rot = 1;
-                        if (g2 > 1e-16 * ab) any_big = 1;         // cosine between the columns above 1e-8
+                        atomicOr(&any_rot, 1);                    // (atomics: several half-warps raise the same flag)
+                        if (g2 > 1e-16 * ab) atomicOr(&any_big, 1);   // cosine between the columns above 1e-8
                     }
                 }
             }

@@ -43,7 +43,7 @@ def _oracle_bond(oracle, cs, phi, counts, j, going_left, chi_max, eta):
 
 
 @pytest.mark.parametrize("N,T,d,chi,grad_kernel,bonds", [
-    (2048, 10, 12, 40, GRAD_KR, (3, 4, 5, 6)),        # config B bond shape: register-operand gradient, krao_reg<5>, p = 80
+    (2048, 10, 12, 40, GRAD_KR, (3, 4, 5, 6)),        # config B bond shape: register-operand gradient, krao_slab<NI=5>, p = 80
     (1024, 8, 16, 64, None, (2, 3, 4)),               # config C (north star) bond shape: 2048 x 1024 split, p = 112
 ])
 def test_teacher_forced_bonds_at_benchmark_shapes(ctx, oracle, pkg, N, T, d, chi, grad_kernel, bonds):
@@ -77,10 +77,7 @@ def test_teacher_forced_bonds_at_benchmark_shapes(ctx, oracle, pkg, N, T, d, chi
         seen_subspace += 1
         if grad_kernel is not None:
             assert gk == grad_kernel
-        if chi <= 48:
-            assert (kk, kv) == (KRAO_REG, (chi + 7) // 8)
-        else:
-            assert kk == KRAO_SLAB
+        assert kk == KRAO_SLAB and kv // 100 == (chi + 7) // 8      # krao_slab_kernel, chi/8 column fragments
     assert seen_subspace == len(bonds)
 
 
@@ -155,7 +152,46 @@ def test_subspace_svd_cutoff_decided_truncation(ctx, oracle, d, chi, C, knee, r1
     assert len(sig7) == len(rs) and np.abs(sig7 - 7.0 * rs).max() < 1e-9 * rs.max()
 
 
-@pytest.mark.parametrize("d,chi", [(16, 64), (12, 64), (8, 52), (16, 128)])
+@pytest.mark.parametrize("d,chi,C,rank", [(12, 40, 2, 24), (16, 64, 2, 40), (12, 40, 2, 70)])
+def test_subspace_svd_rank_deficient_bond(ctx, oracle, d, chi, C, rank):
+    """A numerically rank-deficient bond (a chi_init start, or a tail below rounding level): the Cholesky-QR steps deflate
+    the dependent columns instead of abandoning the subspace path; kept dimension / sigma / product as LAPACK."""
+    rng = np.random.default_rng(rank)
+    m, n = chi * C * d, d * chi
+    U, _ = np.linalg.qr(rng.standard_normal((m, rank)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, rank)))
+    M = (U * (0.8 ** np.arange(rank))) @ V.T
+    M /= np.linalg.norm(M)
+    B = np.ascontiguousarray(M.reshape(chi, C, d, d, chi).transpose(1, 4, 3, 0, 2).reshape(C, -1).T)
+    c_l, c_r, sig = ctx.bond_split(B, d, chi, chi, True, chi)
+    path, restarts = ctx.debug_get("svd_path"), ctx.debug_get("svd_restarts")
+    r_l, r_r, rs = oracle.decompose_bt(B, (chi, d, chi), True, chi, 1e-10)
+    assert len(sig) == len(rs) <= min(rank, chi), (len(sig), len(rs))
+    assert np.abs(sig - rs).max() < 1e-10 * rs.max()
+    ein = "asmc,mtb->btasc"
+    assert np.abs(np.einsum(ein, c_l, c_r) - np.einsum(ein, r_l, r_r)).max() < 1e-10
+    assert path == SVD_SUBSPACE and restarts == 0, (path, restarts)
+
+
+def test_svd_graph_replay_equals_plain_launches(ctx, oracle):
+    """The captured CUDA graph of a subspace round replays exactly the launches it recorded: bit-identical cores with
+    the graph, without it, and with the serial (single-stream) loop's Gram / Cholesky order where that applies."""
+    rng = np.random.default_rng(5)
+    d, chi, C = 12, 40, 2
+    B = _decaying_bond(rng, d, chi, chi, C, 0, 0.9, 0.9)
+    outs = []
+    try:
+        for nograph in (0, 1, 0):
+            ctx.debug_set("SVD_NOGRAPH", nograph)
+            outs.append(ctx.bond_split(B, d, chi, chi, True, chi))
+            assert ctx.debug_get("svd_path") == SVD_SUBSPACE
+    finally:
+        ctx.debug_set("SVD_NOGRAPH", 0)
+    for o in outs[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(outs[0], o))
+
+
+@pytest.mark.parametrize("d,chi", [(16, 64), (12, 64), (8, 52), (16, 128), (12, 40), (24, 32)])
 def test_krao_slab_kernel(ctx, oracle, d, chi):
     """K6/K7 for wide outputs: krao_slab_kernel (W streamed in K-slabs, register operands) vs the oracle and vs the
     shared-memory tile kernel it replaces (MPST_KRAO_NOSLAB), both row-block sizes."""
@@ -187,31 +223,35 @@ def test_krao_slab_kernel(ctx, oracle, d, chi):
 def test_krao_reg_kernel_all_widths(ctx, oracle, chi):
     """K6/K7 register-operand kernel krao_reg_kernel<NI> for NI = 3..6 (17..48 outputs): environments through a
     uniform-chi chain vs the oracle."""
-    N, T, d, C = 600, 5, 8, 2
-    rng = np.random.default_rng(chi)
-    X = rng.uniform(-1, 1, (T, N))
-    phi = oracle.encode(X.T, d)
-    cores = oracle.random_start_mps(T, d, chi, C, seed=chi)
-    ctx.model_init(T, C, d, chi)
-    ctx.set_cores(cores)
-    yh, am = ctx.overlaps(X_TxN=X)
-    ref = oracle.overlaps(cores, phi)
-    assert np.abs(yh - ref).max() < 1e-12 * np.abs(ref).max()
-    assert np.array_equal(am, np.argmax(ref * ref, axis=1))
-    # the training-side environment chain of the same model (mpst_build_env -> K6) takes the register kernel
-    counts = np.array([N // 2, N - N // 2])
-    ctx.train_load_x(X, counts, d, chi)
-    ctx.set_cores(cores)
-    ctx.debug_set("krao_reg_mask", 0)
-    ctx.build_env(True)
-    assert ctx.debug_get("krao_reg_mask") & (1 << ((chi + 7) // 8)), ctx.debug_get("krao_reg_mask")
-    lo, gn, k = ctx.bond_step(T - 2, True, ctx_opts(chi))
-    L = np.ones((N, 1))
-    for j in range(T - 2):
-        L = oracle.env_step_left(phi[:, j], L, cores[j])
-    B, dims = oracle.flatten_bt(cores[T - 2], cores[T - 1])
-    lo_r, G_r = oracle.loss_grad_KLD(B, L, np.ones((N, 1)), phi[:, T - 2], phi[:, T - 1], counts)
-    assert abs(lo - lo_r) <= RTOL * abs(lo_r) and abs(gn - np.linalg.norm(G_r)) <= RTOL * np.linalg.norm(G_r)
+    ctx.debug_set("KRAO_SLAB_MIN", 1000)          # the slab kernel would take chi = 32, 40, 48
+    try:
+        N, T, d, C = 600, 5, 8, 2
+        rng = np.random.default_rng(chi)
+        X = rng.uniform(-1, 1, (T, N))
+        phi = oracle.encode(X.T, d)
+        cores = oracle.random_start_mps(T, d, chi, C, seed=chi)
+        ctx.model_init(T, C, d, chi)
+        ctx.set_cores(cores)
+        yh, am = ctx.overlaps(X_TxN=X)
+        ref = oracle.overlaps(cores, phi)
+        assert np.abs(yh - ref).max() < 1e-12 * np.abs(ref).max()
+        assert np.array_equal(am, np.argmax(ref * ref, axis=1))
+        # the training-side environment chain of the same model (mpst_build_env -> K6) takes the register kernel
+        counts = np.array([N // 2, N - N // 2])
+        ctx.train_load_x(X, counts, d, chi)
+        ctx.set_cores(cores)
+        ctx.debug_set("krao_reg_mask", 0)
+        ctx.build_env(True)
+        assert ctx.debug_get("krao_reg_mask") & (1 << ((chi + 7) // 8)), ctx.debug_get("krao_reg_mask")
+        lo, gn, k = ctx.bond_step(T - 2, True, ctx_opts(chi))
+        L = np.ones((N, 1))
+        for j in range(T - 2):
+            L = oracle.env_step_left(phi[:, j], L, cores[j])
+        B, dims = oracle.flatten_bt(cores[T - 2], cores[T - 1])
+        lo_r, G_r = oracle.loss_grad_KLD(B, L, np.ones((N, 1)), phi[:, T - 2], phi[:, T - 1], counts)
+        assert abs(lo - lo_r) <= RTOL * abs(lo_r) and abs(gn - np.linalg.norm(G_r)) <= RTOL * np.linalg.norm(G_r)
+    finally:
+        ctx.debug_set("KRAO_SLAB_MIN", 25)
 
 
 def ctx_opts(chi):

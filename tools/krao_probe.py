@@ -16,7 +16,7 @@ ctx = m.Context(0)
 ctx.train_load_x(X, counts, d, chi)
 ctx.set_cores(cores)
 ref = None
-for name, fl in (("slab MI=4", {"KRAO_SLAB_MI": 4}), ("slab MI=2", {"KRAO_SLAB_MI": 2}), ("slab 2x2", {"KRAO_SLAB_MI": 22}), ("tiles", {"KRAO_NOSLAB": 1})):
+for name, fl in (("slab", {}), ("slab MI=4", {"KRAO_SLAB_MI": 4}), ("slab 2x2", {"KRAO_SLAB_MI": 22}), ("reg/tiles", {"KRAO_NOSLAB": 1})):
     for k in ("KRAO_SLAB_MI", "KRAO_NOSLAB"):
         ctx.debug_set(k, fl.get(k, 0))
     ctx.build_env(True)
