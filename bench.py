@@ -587,7 +587,7 @@ def main():
     # CPU baseline on the same workload (rank 0, bounded sample, 1 thread like the reference's own hot loop)
     if rank == 0 and not args.no_cpu_baseline:
         try:
-            n_sample, n_bonds = (256, 5) if w["key"] == "C" else (1024, 8)
+            n_sample, n_bonds = (1024, 8) if w["key"] == "C" else (2048, 12)
             r = cpu_reference_rate(cores_host, data[0], data[1], w, n_sample, n_bonds, 1)
             out["cpu_baseline"] = {
                 "value": r["rate_loop_only"], "unit": "sample-bonds/s", "cores": 1, "kind": "port",

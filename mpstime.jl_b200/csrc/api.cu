@@ -845,15 +845,10 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         ProfScope ps(c, MPST_T_UPDATE);
         TRY(launch_sumsq(c, c->G, D * C, s_gn2));
         if (it == 0 && (loss_out || gradnorm_out)) {
+            // read back WITHOUT a host sync of its own: the copies complete before the split's read-back, whose stream
+            // sync every SVD path ends with; the values are handed out (and checked) there.  One idle gap per bond less.
             CUDA_TRY(c, cudaMemcpyAsync(c->hscal, s_loss, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(c, cudaMemcpyAsync(c->hscal + 1, s_gn2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-            if (loss_out) *loss_out = c->hscal[0];
-            if (gradnorm_out) *gradnorm_out = sqrt(c->hscal[1]);
-            if (!std::isfinite(c->hscal[0]) || !std::isfinite(c->hscal[1])) {
-                c->err = "bond_step: non-finite loss or gradient (yhat hit zero?)";
-                return MPST_E_NUMERIC;
-            }
         }
         TRY(launch_axpy(c, c->B, c->G, D * C, s_gn2, o->eta, o->opt_kind == MPST_OPT_TSGO));
     }
@@ -881,6 +876,16 @@ int mpst_bond_step(mpst_ctx* c, int lid, int going_left, const mpst_train_opts* 
         if (rc_svd != MPST_OK) {
             cudaMemcpyAsync(c->hiscal + 1, c->nonfinite, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
             cudaStreamSynchronize(c->stream);
+        }
+        if (loss_out || gradnorm_out) {
+            if (rc_svd != MPST_OK) cudaStreamSynchronize(c->stream);
+            if (loss_out) *loss_out = c->hscal[0];
+            if (gradnorm_out) *gradnorm_out = sqrt(c->hscal[1]);
+            if (!std::isfinite(c->hscal[0]) || !std::isfinite(c->hscal[1])) {
+                c->err = "bond_step: non-finite loss or gradient (yhat hit zero?)";
+                c->hiscal[1] = 0;
+                return MPST_E_NUMERIC;
+            }
         }
         if (c->hiscal[1]) {
             char b[160];

@@ -468,7 +468,7 @@ sym_eig_kernel(const double* __restrict__ H, int splits, int q, int p, double* _
                     xb[t] = in ? hb[16 * t] : 0.0;
                     ga = fma(xa[t], xb[t], ga);
                 }
-                const double al = nrm[ca], be = nrm[cb];
+                const double al = active ? nrm[ca] : 0.0, be = active ? nrm[cb] : 0.0;
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) ga += __shfl_xor_sync(0xffffffffu, ga, o, 16);
                 const double g2 = ga * ga, ab = al * be;
