@@ -119,6 +119,14 @@ sym_eig_reg_kernel(const double* __restrict__ Lm, double* __restrict__ W, double
         __syncwarp();
     };
 
+#ifdef MPST_KDEBUG
+    long long tk[6] = {0, 0, 0, 0, 0, 0}, tq = 0;
+#define TK0() tq = clock64()
+#define TK(i) do { const long long t_ = clock64(); tk[i] += t_ - tq; tq = t_; } while (0)
+#else
+#define TK0()
+#define TK(i)
+#endif
     int sweep = 0;
     for (; sweep < 60; sweep++) {
         if (sweep > 0) refresh_norms();
@@ -127,6 +135,7 @@ sym_eig_reg_kernel(const double* __restrict__ Lm, double* __restrict__ W, double
         for (int ph = 0; ph < P / 2; ph++) {
             // ---- phase A: (0,1) (2,3) (4,5) (6,7) ----
             {
+                TK0();
                 double gam[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -137,7 +146,9 @@ sym_eig_reg_kernel(const double* __restrict__ Lm, double* __restrict__ W, double
                 }
                 const double al = idx == 0 ? nrm[0] : idx == 1 ? nrm[2] : idx == 2 ? nrm[4] : nrm[6];
                 const double be = idx == 0 ? nrm[1] : idx == 1 ? nrm[3] : idx == 2 ? nrm[5] : nrm[7];
+                TK(0);
                 solve4(gam, al, be);
+                TK(1);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const double2 cs = *reinterpret_cast<const double2*>(&prm[g][k][0]);
@@ -152,6 +163,7 @@ sym_eig_reg_kernel(const double* __restrict__ Lm, double* __restrict__ W, double
                     nrm[2 * k + 1] = nn.x;
                 }
                 __syncwarp();                                            // prm is rewritten in phase B
+                TK(2);
             }
             // ---- phase B: (7 of the left neighbour | 0) (1,2) (3,4) (5,6) ----
             {
@@ -161,6 +173,7 @@ sym_eig_reg_kernel(const double* __restrict__ Lm, double* __restrict__ W, double
                     if (l16 == 0) xb[g][P] = nrm[7];
                 }
                 __syncthreads();
+                TK(3);
                 double e[NR], ne = 0.0;
 #pragma unroll
                 for (int r = 0; r < NR; r++) e[r] = g > 0 ? xb[g > 0 ? g - 1 : 0][l16 + 16 * r] : 0.0;
@@ -207,17 +220,24 @@ sym_eig_reg_kernel(const double* __restrict__ Lm, double* __restrict__ W, double
                     nrm[2 * k - 1] = nn.y;
                     nrm[2 * k] = nn.x;
                 }
+                TK(4);
                 __syncthreads();
                 if (g < NG - 1) {
 #pragma unroll
                     for (int r = 0; r < NR; r++) x[7][r] = xb[g][l16 + 16 * r];
                     nrm[7] = xb[g][P];
                 }
+                TK(5);
             }
         }
         // quadratic convergence: a sweep whose largest rotated cosine was <= 1e-8 leaves cosines at ~1e-16
         if (!__syncthreads_or(big ? 1 : 0)) { sweep++; break; }
     }
+#ifdef MPST_KDEBUG
+    if (tid == 0 || tid == 32 * (NR - 1))
+        printf("[eig_reg p=%d tid=%d sweeps=%d] A: dots %lld  reduce+params+bcast %lld  rotate %lld | B: publish+sync %lld  compute %lld  sync+readback %lld (cycles)\n",
+               P, tid, sweep, tk[0], tk[1], tk[2], tk[3], tk[4], tk[5]);
+#endif
     if (tid == 0) {
         if (sweep >= 60) atomicOr(status, 2);
         status[1] = sweep;

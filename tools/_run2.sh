@@ -4,7 +4,7 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --mast
 tail -2 gpurun_out/r02_bench_n2.err
 python - <<PYEOF
 import json
-d=json.load(open("gpurun_out/r02_bench_n2.json"))
+d=json.loads([l for l in open("gpurun_out/r02_bench_n2.json").read().splitlines() if l.startswith("{")][-1])
 st=lambda s:{k:v for k,v in s.items() if k!="note"}
 print("N=2 value",d["value"],"ms/bond",d["ms_per_bond"],"e2e",d["e2e"]["value"],"frac",d["roofline"]["frac"], st(d["svd_stats"]))
 print(d["device_time_breakdown_ms"])
