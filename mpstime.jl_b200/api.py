@@ -268,14 +268,24 @@ def build_encoding_table(opts, Xs_sorted_TxN):
 
 
 def _normalize(cores):
-    """normalize!(W) (RealRealHighDimension.jl:852): unit norm, scale spread over all cores."""
-    E = np.ones((1, 1, 1))
+    """normalize!(W) (RealRealHighDimension.jl:852): unit norm, scale spread over all cores.  Transfer matrices
+    E' = sum_s A_s^T E A_s as two BLAS contractions per site (np.einsum's three-operand loop took seconds at chi = 40);
+    the running matrix is rescaled at every site so that long chains neither overflow nor underflow."""
+    E = np.ones((1, 1, 1))                                     # (a, b, class)
+    logn = 0.0
     for A in cores:
-        if A.ndim == 4:
-            E = np.einsum("ab,asmc,bsnc->mnc", E[:, :, 0], A, A)
+        if A.ndim == 4:                                        # label core: (a, s, m, c), E has no class axis yet
+            E2 = E[:, :, 0]
+            En = np.stack([np.tensordot(A[..., c], np.tensordot(E2, A[..., c], axes=([1], [0])), axes=([0, 1], [0, 1]))
+                           for c in range(A.shape[3])], axis=2)
         else:
-            E = np.einsum("abc,asm,bsn->mnc", E, A, A)
-    z = np.exp(0.5 * np.log(float(E[0, 0, :].sum())) / len(cores))
+            En = np.stack([np.tensordot(A, np.tensordot(E[:, :, c], A, axes=([1], [0])), axes=([0, 1], [0, 1]))
+                           for c in range(E.shape[2])], axis=2)
+        sc = float(np.abs(En).max())
+        sc = sc if sc > 0.0 else 1.0
+        E = En / sc
+        logn += np.log(sc)
+    z = np.exp(0.5 * (logn + np.log(float(E[0, 0, :].sum()))) / len(cores))
     return [A / z for A in cores]
 
 
