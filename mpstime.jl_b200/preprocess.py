@@ -67,8 +67,8 @@ def transform_train_data(X, opts):
     X = np.asarray(X, dtype=np.float64)
     norms = Norms()
     if opts.sigmoid_transform:
-        q75, q25 = np.quantile(X, [0.75, 0.25])
-        norms.sigmoid = (float(np.median(X)), float(q75 - q25))
+        q25, med, q75 = np.quantile(X, [0.25, 0.5, 0.75])      # one partition pass; quantile(0.5) == median
+        norms.sigmoid = (float(med), float(q75 - q25))
     Xs = Norms(norms.sigmoid, None).apply(X)
     if opts.minmax:
         norms.minmax = (float(Xs.min()), float(Xs.max()))

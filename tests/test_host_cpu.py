@@ -256,3 +256,23 @@ def test_streamk_schedule_builder(tmp_path):
                            os.path.join(ROOT, "tests", "cpp", "streamk_check.cpp"), "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "STREAMK_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_normalize_matches_direct_contraction(pkg):
+    """api._normalize (normalize!(W), RealRealHighDimension.jl:852) through BLAS contractions with a running rescale
+    equals the direct three-operand contraction, label core anywhere in the chain, and yields <W|W> = 1."""
+    api = sys.modules[pkg.MPSOptions.__module__]
+    rng = np.random.default_rng(0)
+    T, chi, d, C = 9, 6, 3, 2
+    for pos in (0, 4, T - 1):
+        cores = []
+        for j in range(T):
+            cl, cr = (1 if j == 0 else chi), (1 if j == T - 1 else chi)
+            cores.append(rng.standard_normal((cl, d, cr, C)) if j == pos else rng.standard_normal((cl, d, cr)))
+        out = api._normalize(cores)
+        E = np.ones((1, 1, 1))
+        for A in out:
+            E = np.einsum("ab,asmc,bsnc->mnc", E[:, :, 0], A, A) if A.ndim == 4 else np.einsum("abc,asm,bsn->mnc", E, A, A)
+        assert abs(float(E[0, 0, :].sum()) - 1.0) < 1e-12
+        ratio = out[0].ravel()[0] / cores[0].ravel()[0]
+        assert all(np.allclose(o, c * ratio, rtol=1e-13, atol=0) for o, c in zip(out, cores))
