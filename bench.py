@@ -612,23 +612,25 @@ def main():
 
     # the reference-facing call itself: fitMPS(X_train, y_train, X_test, y_test, opts) with the reference's default
     # log_level = 3 (per-sweep train / test loss, KL divergence, accuracy, confusion on the device), raw host arrays in,
-    # trained MPS out -- one sweep of configs[1], host preprocessing and every read-back inside the timed region
+    # trained MPS out -- three sweeps of configs[1], host preprocessing and every read-back inside the timed region
     if world == 1 and w["key"] == "C" and not args.no_config_b and out.get("config_B", {}).get("value"):
         try:
             wb = WORKLOADS["B"]
             Xb, yb = make_data(wb["N"], wb["T"], 77, wb)
             Xt, yt = make_data(10_000, wb["T"], 78, wb)
-            ob = m.MPSOptions(d=wb["d"], chi_max=wb["chi_max"], eta=wb["eta"], nsweeps=1, log_level=3, verbosity=-1)
+            nsw = 3
+            ob = m.MPSOptions(d=wb["d"], chi_max=wb["chi_max"], eta=wb["eta"], nsweeps=nsw, log_level=3, verbosity=-1)
             t0 = time.time()
             mps, info, _ = m.fitMPS(Xb, yb, Xt, yt, ob, device=local)
             dt = time.time() - t0
             nb = 2 * (wb["T"] - 1)
             out["config_B"]["api_fitMPS"] = {
-                "value": nb * wb["N"] / dt, "unit": "sample-bonds/s", "seconds": dt, "sweeps": 1,
+                "value": nsw * nb * wb["N"] / dt, "unit": "sample-bonds/s", "seconds": dt, "sweeps": nsw,
                 "train_acc": float(info["train_acc"][-1]), "test_acc": float(info["test_acc"][-1]),
-                "note": "wall clock of one fitMPS call (N = 100k train + 10k test, T = 100, d = 12, chi_max = 40, 1 sweep, log_level = 3): "
-                        "normalisation + class sort on the host, series upload, start MPS, 198 bond updates driven one C-ABI call "
-                        "at a time, 3 evaluations of both sets on the device, normalize!, cores read back"}
+                "note": "wall clock of one fitMPS call (N = 100k train + 10k test, T = 100, d = 12, chi_max = 40, 3 sweeps from a random "
+                        "chi_init = 4 start, log_level = 3): normalisation + class sort on the host, series upload, start MPS, "
+                        "3 x 198 bond updates driven one C-ABI call at a time, 5 evaluations of both sets on the device, "
+                        "normalize!, cores read back"}
         except Exception as e:
             out["config_B"]["api_fitMPS"] = {"value": None, "error": repr(e)}
 
