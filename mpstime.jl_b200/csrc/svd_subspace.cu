@@ -993,7 +993,7 @@ restart:
         // iterations of the first round: 7 (5 when the subspace has 2k columns) unless this bond's previous visits
         // showed what reaches the residual bound (trained spectra change slowly from sweep to sweep)
         const int slot = (c->svd_slot >= 0 && c->svd_slot < (int)c->svd_its.size()) ? c->svd_slot : -1;
-        int first = c->flag[F_SVD_IT] > 0 ? c->flag[F_SVD_IT] : (p >= 2 * k ? 5 : 7);
+        int first = c->flag[F_SVD_IT] > 0 ? c->flag[F_SVD_IT] : (p >= 2 * k ? 5 : c->flag[F_SVD_FIRST]);
         const bool hinted = slot >= 0 && c->svd_its[slot] == 0 && c->flag[F_SVD_IT] <= 0 && c->svd_hint_its > 0 &&
                             c->svd_hint_m == m && c->svd_hint_n == n;
         if (slot >= 0 && c->svd_its[slot] > 0 && c->flag[F_SVD_IT] <= 0) first = c->svd_its[slot];
