@@ -218,11 +218,11 @@ const FlagDef kFlags[F_COUNT] = {
     {"SVD_PB64", 0, true}, {"SVD_LEGACY", 0, true}, {"SVD_NOSUB", 0, true}, {"SVD_OVS", 0, false},
     {"SVD_NOHALF", 0, true}, {"SVD_HALF_FROM", 1, false}, {"SVD_IT", 0, false}, {"SVD_NOGRAPH", 0, true},
     {"GRAD_KC", 0, false}, {"IMPUTE_NOSERIES", 0, true}, {"IMPUTE_FULLSYM", 0, true}, {"GRAD_PHASES", 0, false},
-    {"SVD_EIGSMEM", 0, true}, {"SVD_SERIAL", 0, true}, {"SVD_CHOLSEQ", 0, true}, {"SVD_PROBE", 0, true}, {"SVD_SYNCFIRST", 0, true}, {"SVD_NOPREP", 0, true}, {"KRAO_NOSLAB", 0, true}, {"KRAO_SLAB_MI", 0, false}, {"KRAO_SLAB_MIN", 25, false}, {"SVD_FIRST", 7, false},
+    {"SVD_EIGSMEM", 0, true}, {"SVD_SERIAL", 0, true}, {"SVD_CHOLSEQ", 0, true}, {"SVD_PROBE", 0, true}, {"SVD_SYNCFIRST", 0, true}, {"SVD_NOPREP", 0, true}, {"KRAO_NOSLAB", 0, true}, {"KRAO_SLAB_MI", 0, false}, {"KRAO_SLAB_MIN", 25, false}, {"SVD_FIRST", 7, false}, {"SVD_NO2PASS", 0, true},
 };
 const char* kLast[L_COUNT] = {"svd_path", "svd_iters", "svd_restarts", "grad_kernel", "grad_variant", "krao_kernel",
                               "krao_variant", "fwd_path", "krao_reg_mask", "grad_kr_launches", "grad_tile_launches", "svd_calls",
-                              "svd_iters_sum", "svd_round2", "svd_jacobi", "svd_fast", "svd_serial", "krao_slab_launches"};
+                              "svd_iters_sum", "svd_round2", "svd_jacobi", "svd_fast", "svd_serial", "krao_slab_launches", "svd_twopass"};
 void flags_from_env(mpst_ctx* c) {
     for (int f = 0; f < F_COUNT; f++) {
         c->flag[f] = kFlags[f].def;
@@ -330,7 +330,7 @@ int mpst_destroy(mpst_ctx* c) {
     free_training(c, true);
     auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(c->B); fr(c->G); fr(c->Z); fr(c->part); fr(c->red); fr(c->scal); fr(c->S); fr(c->gpart); fr(c->wbuf);
-    fr(c->colnorm); fr(c->tmp); fr(c->meta); fr(c->sub); fr(c->gws); fr(c->gws2); fr(c->kslab);
+    fr(c->colnorm); fr(c->tmp); fr(c->meta); fr(c->sub); fr(c->stbuf); fr(c->gws); fr(c->gws2); fr(c->kslab);
     if (c->enc.ip) cudaFree(c->enc.ip);
     if (c->enc.dp) cudaFree(c->enc.dp);
     for (int i = 0; i < 16; i++) if (c->imp_ptr[i]) cudaFree(c->imp_ptr[i]);

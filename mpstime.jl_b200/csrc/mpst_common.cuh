@@ -45,7 +45,7 @@ struct Timer {
 enum {
     F_DENSE_FWD = 0, F_NO_ENV_REUSE, F_GRAD_T128, F_GRAD_NOKR, F_IMPUTE_NODBUF, F_IMPUTE_DEBUG, F_KRAO_NOREG,
     F_SVD_INNER, F_SVD_DEBUG, F_SVD_SKIP, F_SVD_FIXED, F_SVD_FULL, F_SVD_PB64, F_SVD_LEGACY, F_SVD_NOSUB, F_SVD_OVS,
-    F_SVD_NOHALF, F_SVD_HALF_FROM, F_SVD_IT, F_SVD_NOGRAPH, F_GRAD_KC, F_IMPUTE_NOSERIES, F_IMPUTE_FULLSYM, F_GRAD_PHASES, F_SVD_EIGSMEM, F_SVD_SERIAL, F_SVD_CHOLSEQ, F_SVD_PROBE, F_SVD_SYNCFIRST, F_SVD_NOPREP, F_KRAO_NOSLAB, F_KRAO_SLAB_MI, F_KRAO_SLAB_MIN, F_SVD_FIRST, F_COUNT
+    F_SVD_NOHALF, F_SVD_HALF_FROM, F_SVD_IT, F_SVD_NOGRAPH, F_GRAD_KC, F_IMPUTE_NOSERIES, F_IMPUTE_FULLSYM, F_GRAD_PHASES, F_SVD_EIGSMEM, F_SVD_SERIAL, F_SVD_CHOLSEQ, F_SVD_PROBE, F_SVD_SYNCFIRST, F_SVD_NOPREP, F_KRAO_NOSLAB, F_KRAO_SLAB_MI, F_KRAO_SLAB_MIN, F_SVD_FIRST, F_SVD_NO2PASS, F_COUNT
 };
 // which code path the last call took (mpst_debug_get): lets the parity tests assert that they exercised the
 // kernels the benchmark runs, and lets bench.py name the kernel it reports a roofline for
@@ -68,6 +68,7 @@ enum {
     L_SVD_FAST,
     L_SVD_SERIAL,         // fast-path splits that ran the serial (fully orthonormalising) loop
     L_KRAO_SLAB_LAUNCHES, // launches of krao_slab_kernel since last cleared
+    L_SVD_TWOPASS,        // fast-path splits that needed the deflated second pass (chi_max > 80)
     L_COUNT
 };
 
@@ -145,6 +146,15 @@ struct mpst_ctx {
     int* perm = nullptr;        // [npad]
     double* sub = nullptr;      // subspace-SVD workspace
     size_t subcap = 0;
+    // deflated two-pass split (chi_max > 80, svd_subspace.cu): while st_on, a finished subspace pass hands its triplets to
+    // the staging blocks stU (m x k, U S) / stV (n x k) / stP (sigma^2) at column st_col0 instead of writing cores;
+    // st_kept = device scalar holding the weight the first pass kept (nullptr during the first pass)
+    bool st_on = false;
+    int st_col0 = 0;
+    double* st_kept = nullptr;
+    double *stU = nullptr, *stV = nullptr, *stP = nullptr;
+    double* stbuf = nullptr;
+    size_t stbufcap = 0;
     double* gws = nullptr;      // split-K partial products of the small GEMMs
     double* kslab = nullptr;    // K6: slab-major copy of the weight matrix (krao_slab.cu)
     size_t kslabcap = 0;

@@ -598,7 +598,8 @@ colscale_kernel(const double* __restrict__ in, double* __restrict__ out, int row
 // (trace - sum) already discarded; perm[k] = column of the k-th largest, Psorted, iscal[0] = chi_new.
 __global__ void __launch_bounds__(256)
 ritz_trunc_kernel(const double* __restrict__ ev, int p, int n_total, const double* __restrict__ trace_dev, int maxdim,
-                  double cutoff, int* __restrict__ perm, double* __restrict__ Psorted, int* __restrict__ iscal) {
+                  double cutoff, int* __restrict__ perm, double* __restrict__ Psorted, int* __restrict__ iscal,
+                  const double* __restrict__ kept_dev = nullptr) {
     for (int j = threadIdx.x; j < p; j += blockDim.x) {
         const double pj = ev[j];
         int rank = 0;
@@ -615,12 +616,15 @@ ritz_trunc_kernel(const double* __restrict__ ev, int p, int n_total, const doubl
         for (int q = 0; q < p; q++) sum += Psorted[q];
         double scale = trace_dev ? *trace_dev : 1.0;
         if (!(scale > 0.0)) scale = 1.0;
-        double err = fmax(scale - sum, 0.0);               // everything outside the Ritz subspace
+        // kept_dev (second pass of a deflated split): weight already kept by the first pass; this pass may keep nothing
+        const double kept = kept_dev ? *kept_dev : 0.0;
+        double err = fmax(scale - kept - sum, 0.0);        // everything outside the Ritz subspace
         (void)n_total;
         int keep = p;
         while (keep > maxdim) { err += Psorted[keep - 1]; keep--; }
-        while (keep > 1 && err + Psorted[keep - 1] <= cutoff * scale) { err += Psorted[keep - 1]; keep--; }
-        iscal[0] = max(keep, 1);
+        const int floor_keep = kept_dev ? 0 : 1;
+        while (keep > floor_keep && err + Psorted[keep - 1] <= cutoff * scale) { err += Psorted[keep - 1]; keep--; }
+        iscal[0] = max(keep, floor_keep);
     }
 }
 
@@ -645,10 +649,13 @@ __global__ void scatter_label_kernel(const double* __restrict__ UkSk, int m, int
     }
 }
 
-// res = max_i || T2[:, i] - P_i * Vk[:, i] || / P_0   over the kept columns
+// res = max_i || T2[:, i] - P_i * Vk[:, i] || / P_0   over the kept columns.  scale_dev (second pass of a deflated
+// split): sigma_1^2 of the whole matrix from the first pass -- the deflated matrix carries the first pass's rounding
+// noise (eps sigma_1 per entry), so its own leading value is the wrong yardstick.
 __global__ void __launch_bounds__(256)
 residual_kernel(const double* __restrict__ T2, const double* __restrict__ Vk, const double* __restrict__ Psorted,
-                const int* __restrict__ iscal, int n, unsigned long long* __restrict__ out_bits) {
+                const int* __restrict__ iscal, int n, unsigned long long* __restrict__ out_bits,
+                const double* __restrict__ scale_dev = nullptr) {
     __shared__ double sh[8];
     const int i = blockIdx.x;
     if (i >= iscal[0]) return;
@@ -665,7 +672,7 @@ residual_kernel(const double* __restrict__ T2, const double* __restrict__ Vk, co
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < 8; w++) t += sh[w];
-        const double rel = sqrt(t) / fmax(Psorted[0], 1e-300);
+        const double rel = sqrt(t) / fmax(scale_dev ? *scale_dev : Psorted[0], 1e-300);
         atomicMax(out_bits, (unsigned long long)__double_as_longlong(rel));
     }
 }
@@ -687,6 +694,36 @@ __global__ void scale_cols_sqrt_kernel(double* __restrict__ Uk, int m, const dou
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x)
         Uk[e] *= sqrt(fmax(Psorted[(int)(e / m)], 0.0));
 }
+
+// ---- deflated two-pass split (chi_max > 80) ----
+// out[0] = sum of the first cnt entries (fixed order)
+__global__ void sum_first_kernel(const double* __restrict__ P, int cnt, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int q = 0; q < cnt; q++) s += P[q];
+        out[0] = s;
+    }
+}
+// T <- M - T   (m x n; M with leading dimension ldm, T dense)
+__global__ void __launch_bounds__(256)
+deflate_kernel(const double* __restrict__ M, int64_t ldm, double* __restrict__ T, int m, int n) {
+    const int64_t tot = (int64_t)m * n;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = e / m, i = e - j * m;
+        T[e] = M[i + ldm * j] - T[e];
+    }
+}
+// scatter_label_kernel with the kept dimension known on the host; also leaves it in iscal[0]
+__global__ void scatter_label_n_kernel(const double* __restrict__ UkSk, int m, int Dx, int chi, int* __restrict__ iscal,
+                                       double* __restrict__ label_core) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) iscal[0] = chi;
+    const int64_t tot = (int64_t)m * chi;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int kk = (int)(e / m), r = (int)(e % m);
+        const int cls = r / Dx, xx = r - cls * Dx;
+        label_core[(size_t)cls * Dx * chi + xx + (size_t)Dx * kk] = UkSk[e];
+    }
+}
 }  // namespace
 
 // M: column-major m x n (leading dimension ldm) on the device, already scaled.  trace_dev: ||M||_F^2 on the
@@ -698,9 +735,9 @@ __global__ void scale_cols_sqrt_kernel(double* __restrict__ Uk, int m, const dou
 //   subspace   (otherwise)         : block subspace iteration, H = (M Q)^T (M Q)
 // Working with sigma^2 resolves weights down to eps*sigma_1^2, so these paths are used only when the
 // truncation cutoff is >= 1e-12 (the reference default is 1e-10); smaller cutoffs take the exact Jacobi.
-int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n, int C, int chi_max, double cutoff,
-                        const double* trace_dev, double* label_core, double* ortho_core, int* chi_new,
-                        double* sigma_host, bool* done) {
+static int subspace_core(mpst_ctx* c, const double* M, int64_t ldm, int m, int n, int C, int chi_max, double cutoff,
+                         const double* trace_dev, double* label_core, double* ortho_core, int* chi_new,
+                         double* sigma_host, bool* done) {
     *done = false;
     c->last[L_SVD_RESTARTS] = 0;
     if (c->flag[F_SVD_NOSUB] || cutoff < 1e-12) return MPST_OK;
@@ -748,6 +785,18 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         c->last[L_SVD_PATH] = mode == 0 ? 1 : (mode == 1 ? 2 : 3);
         c->last[L_SVD_ITERS] = iters;
         c->last[L_SVD_ITERS_SUM] += iters;
+        if (c->st_on) {
+            // one pass of a deflated two-pass split: hand the triplets to the staging blocks, the caller assembles the cores
+            const size_t col0 = (size_t)c->st_col0;
+            if (*chi_new > 0) {
+                CUDA_TRY(c, cudaMemcpyAsync(c->stU + (size_t)m * col0, Uk, sizeof(double) * (size_t)m * (*chi_new), cudaMemcpyDeviceToDevice, c->stream));
+                CUDA_TRY(c, cudaMemcpyAsync(c->stV + (size_t)n * col0, Vs, sizeof(double) * (size_t)n * (*chi_new), cudaMemcpyDeviceToDevice, c->stream));
+                CUDA_TRY(c, cudaMemcpyAsync(c->stP + col0, ev + p, sizeof(double) * (*chi_new), cudaMemcpyDeviceToDevice, c->stream));
+            }
+            if (dbg) fprintf(stderr, "[svd %s, pass at column %d] m=%d n=%d p=%d iters=%d chi=%d residual=%.2e\n", what, c->st_col0, m, n, p, iters, *chi_new, res);
+            *done = true;
+            return MPST_OK;
+        }
         c->last[L_SVD_FAST]++;
         if (mode == 2) CUDA_TRY(c, cudaMemcpyAsync(ortho_core, Vs, sizeof(double) * (size_t)n * (*chi_new), cudaMemcpyDeviceToDevice, c->stream));
         scatter_label_kernel<<<2 * c->sm_count, 256, 0, c->stream>>>(Uk, m, m / C, c->iscal, label_core);
@@ -914,7 +963,7 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         if (c->flag[F_SVD_EIGSMEM] || !launch_sym_eig_reg(p, Lm, Wm, ev, status, c->stream))
             if (launch_sym_eig<true>(p, eig_smem, Lm, 1, p, Wm, ev, status, c->stream)) CUDA_TRY(c, cudaGetLastError());
         c->launches++;
-        ritz_trunc_kernel<<<1, 256, 0, c->stream>>>(ev, p, n, trace_dev, chi_max, cutoff, c->perm, ev + p, c->iscal);
+        ritz_trunc_kernel<<<1, 256, 0, c->stream>>>(ev, p, n, trace_dev, chi_max, cutoff, c->perm, ev + p, c->iscal, c->st_on ? c->st_kept : nullptr);
         gather_cols_kernel<<<(p * k + 255) / 256, 256, 0, c->stream>>>(Wm, p, c->perm, k, Wk);
         c->launches += 3;
         TRY(launch_dgemm(c, 0, 0, n, k, p, qa, n, Wk, p, Vs, n));                 // V_k = Q W_k
@@ -922,7 +971,7 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         // residual of the kept Ritz pairs: M^T (M v_i) - sigma_i^2 v_i
         TRY(launch_dgemm(c, 1, 0, n, k, m, M, ldm, Uk, m, T2, n));
         CUDA_TRY(c, cudaMemsetAsync(resbits, 0, sizeof(unsigned long long), c->stream));
-        residual_kernel<<<k, 256, 0, c->stream>>>(T2, Vs, ev + p, c->iscal, n, resbits);
+        residual_kernel<<<k, 256, 0, c->stream>>>(T2, Vs, ev + p, c->iscal, n, resbits, (c->st_on && c->st_kept) ? c->stP : nullptr);
         c->launches++;
         CUDA_TRY(c, cudaGetLastError());
         // one read-back: chi_new, non-finite flag [0..1], Cholesky / Jacobi status [8..9], residual bits [10..11]
@@ -940,7 +989,8 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         memcpy(&cbits, &cutoff, sizeof cbits);
         std::vector<int64_t> key = {m, n, (int64_t)ldm, p, k, niter, fresh ? 1 : 0, chi_max, (int64_t)cbits, C,
                                     (int64_t)(uintptr_t)M, (int64_t)(uintptr_t)trace_dev, (int64_t)(uintptr_t)c->sub,
-                                    (int64_t)(uintptr_t)c->gws, (int64_t)(uintptr_t)c->gws2, c->flag[F_SVD_CHOLSEQ], c->flag[F_SVD_EIGSMEM]};
+                                    (int64_t)(uintptr_t)c->gws, (int64_t)(uintptr_t)c->gws2, c->flag[F_SVD_CHOLSEQ], c->flag[F_SVD_EIGSMEM], c->st_on ? 1 : 0,
+                                    (int64_t)(uintptr_t)(c->st_on ? c->st_kept : nullptr)};
         SvdGraph* g = nullptr;
         for (auto& e : c->svd_graphs) if (e.key == key) { g = &e; break; }
         if (!g) {
@@ -988,8 +1038,16 @@ int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n,
         c->launches += g->launches;
         return MPST_OK;
     };
+    // Rounds 0..2 are the measured policy of the training sweeps (first, then 3 + 3 iterations).  Where that policy used
+    // to hand the bond to the exact Jacobi (a slowly decaying spectrum on a big matrix: 3.3 s at 6144 x 3072 against
+    // 0.3 ms per iteration), the observed contraction rate now decides: if it predicts convergence within `adaptive_budget`
+    // more iterations the loop goes on with plain launches (no graph: these iteration counts do not repeat).
+    double prev_res = -1.0;
+    int next_n = 3, adaptive_budget = 48;
+    bool adaptive = false;
 restart:
-    for (int round = 0; round < max_rounds; round++) {
+    prev_res = -1.0; next_n = 3; adaptive = false;
+    for (int round = 0; round < max_rounds + 8; round++) {
         // iterations of the first round: 7 (5 when the subspace has 2k columns) unless this bond's previous visits
         // showed what reaches the residual bound (trained spectra change slowly from sweep to sweep)
         const int slot = (c->svd_slot >= 0 && c->svd_slot < (int)c->svd_its.size()) ? c->svd_slot : -1;
@@ -998,12 +1056,13 @@ restart:
                             c->svd_hint_m == m && c->svd_hint_n == n;
         if (slot >= 0 && c->svd_its[slot] > 0 && c->flag[F_SVD_IT] <= 0) first = c->svd_its[slot];
         else if (hinted) first = std::max(c->svd_hint_its, c->svd_floor[slot]);
-        const int niter = round == 0 ? first : 3;
+        const int niter = round == 0 ? first : next_n;
         if (c->svd_prepare_only) {
             if (!dbg && !c->flag[F_SVD_NOGRAPH] && overlap) TRY(run_round(true, niter, 0));
             return MPST_OK;
         }
-        TRY(run_round(iters_done == 0, niter, iters_done));
+        if (adaptive) TRY(enqueue_round(false, niter, iters_done));
+        else TRY(run_round(iters_done == 0, niter, iters_done));
         iters_done += niter;
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         double res;
@@ -1070,10 +1129,91 @@ restart:
             return finish("subspace", iters_done, res);
         }
         if (round == 0) c->last[L_SVD_ROUND2]++;
-        if (res > (round == 0 ? 1e-5 : 1e-10)) {                                   // spectrum too flat: full Jacobi
-            if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d residual %.2e after %d its -> full Jacobi\n", m, n, res, iters_done);
+        if (round < max_rounds - 1 && res <= (round == 0 ? 1e-5 : 1e-10)) { prev_res = res; next_n = 3; continue; }
+        // contraction per iteration: from the last two residuals, or (round 0) from the start at ~1
+        const double rate = (round == 0 || !(prev_res > 0.0)) ? pow(res, 1.0 / niter) : pow(res / prev_res, 1.0 / niter);
+        const int need = (rate > 0.0 && rate < 0.85) ? (int)ceil(log(2e-14 / res) / log(rate)) : 1 << 20;
+        if ((round == 0 && res > 1e-3) || need > adaptive_budget) {               // spectrum too flat: full Jacobi
+            if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d residual %.2e after %d its (rate %.2f) -> full Jacobi\n", m, n, res, iters_done, rate);
             return MPST_OK;
         }
+        next_n = std::min(std::max(need, 3), 16);
+        adaptive_budget -= next_n;
+        adaptive = true;
+        prev_res = res;
+        if (dbg) fprintf(stderr, "[svd subspace] m=%d n=%d residual %.2e after %d its, rate %.2f per iteration -> %d more\n", m, n, res, iters_done, rate, next_n);
     }
     return MPST_OK;                                                                // not converged: full Jacobi
+}
+
+// Entry point.  chi_max <= 80 (or a Gram-path shape): one call of subspace_core.  Larger chi_max: the single-CTA Cholesky
+// and Rayleigh-Ritz kernels stop at 128 columns and a subspace needs chi_max + 32, so the split runs as TWO passes of
+// the same machinery (each on <= 112 columns, the shape the north-star bonds use):
+//   pass 1 : the 64 leading triplets of M (truncation rule with the global trace; fewer than 64 kept => finished),
+//   deflate: M2 = M - (U1 S1) V1^T,
+//   pass 2 : up to chi_max - 64 triplets of M2; the truncation rule continues where pass 1 stopped (weight already kept
+//            = sum sigma_i^2 of pass 1, this pass may keep nothing); residuals measured against sigma_1^2 of M.
+// M2 carries pass 1's rounding (eps sigma_1 per entry): sigma and the truncated product agree with LAPACK to ~1e-15
+// sigma_1, V2 is orthogonal to V1 to eps sigma_1 / sigma_j (1e-12 measured at the cutoff edge).  Any pass that does not
+// converge leaves *done = false and the caller runs the exact Jacobi on the untouched M.
+int svd_subspace_device(mpst_ctx* c, const double* M, int64_t ldm, int m, int n, int C, int chi_max, double cutoff,
+                        const double* trace_dev, double* label_core, double* ortho_core, int* chi_new,
+                        double* sigma_host, bool* done) {
+    *done = false;
+    const int k = std::min(chi_max, std::min(m, n));
+    const int K1 = 64, PMAX = 112;
+    const bool two_pass = k > 80 && n > PMAX && m > PMAX && !c->flag[F_SVD_NO2PASS] && !c->flag[F_SVD_NOSUB] && cutoff >= 1e-12;
+    if (!two_pass) return subspace_core(c, M, ldm, m, n, C, chi_max, cutoff, trace_dev, label_core, ortho_core, chi_new, sigma_host, done);
+    if (c->svd_prepare_only) return MPST_OK;
+    const size_t szU = (size_t)round_up((int64_t)m * k, 32), szV = (size_t)round_up((int64_t)n * k, 32), szP = (size_t)round_up(k + 8, 32);
+    TRY(ensure_buf(c, &c->stbuf, &c->stbufcap, szU + szV + szP + (size_t)m * n));
+    c->stU = c->stbuf;
+    c->stV = c->stU + szU;
+    c->stP = c->stV + szV;
+    double* kept = c->stP + k;
+    double* M2 = c->stP + szP;
+    const int slot_saved = c->svd_slot;                    // the per-bond iteration history belongs to single-pass splits
+    c->svd_slot = -1;
+    c->st_on = true;
+    c->st_col0 = 0;
+    c->st_kept = nullptr;
+    int chi1 = 0, chi2 = 0;
+    bool d1 = false, d2 = true;
+    int rc = subspace_core(c, M, ldm, m, n, C, K1, cutoff, trace_dev, nullptr, nullptr, &chi1, nullptr, &d1);
+    if (rc == MPST_OK && d1 && chi1 == K1) {
+        d2 = false;
+        sum_first_kernel<<<1, 32, 0, c->stream>>>(c->stP, K1, kept);
+        c->launches++;
+        rc = launch_dgemm(c, 0, 1, m, n, K1, c->stU, m, c->stV, n, M2, m);                 // (U1 S1) V1^T
+        if (rc == MPST_OK) {
+            deflate_kernel<<<2 * c->sm_count, 256, 0, c->stream>>>(M, ldm, M2, m, n);
+            c->launches++;
+            c->st_col0 = K1;
+            c->st_kept = kept;
+            rc = subspace_core(c, M2, m, m, n, C, k - K1, cutoff, trace_dev, nullptr, nullptr, &chi2, nullptr, &d2);
+        }
+    }
+    c->st_on = false;
+    c->st_kept = nullptr;
+    c->svd_slot = slot_saved;
+    if (rc != MPST_OK) return rc;
+    if (!d1 || !d2) return MPST_OK;                        // not converged: exact Jacobi on M
+    const int chi = chi1 + chi2;
+    *chi_new = chi;
+    c->hiscal[0] = chi;
+    CUDA_TRY(c, cudaMemcpyAsync(ortho_core, c->stV, sizeof(double) * (size_t)n * chi, cudaMemcpyDeviceToDevice, c->stream));
+    scatter_label_n_kernel<<<2 * c->sm_count, 256, 0, c->stream>>>(c->stU, m, m / C, chi, c->iscal, label_core);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    if (sigma_host) {
+        std::vector<double> tmp(chi);
+        CUDA_TRY(c, cudaMemcpyAsync(tmp.data(), c->stP, sizeof(double) * chi, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        for (int q = 0; q < chi; q++) sigma_host[q] = sqrt(tmp[q]);
+    }
+    c->last[L_SVD_PATH] = 3;
+    c->last[L_SVD_FAST]++;
+    if (chi2 > 0 || chi1 == K1) c->last[L_SVD_TWOPASS]++;
+    *done = true;
+    return MPST_OK;
 }
