@@ -25,6 +25,7 @@
 #include "mpst_common.cuh"
 #include "dmma.cuh"
 #include "encode_device.cuh"
+#include "encode_table_device.cuh"
 
 namespace {
 constexpr int NT = 256;
@@ -55,12 +56,28 @@ struct ImpParams {
     const double* leg_pq;
     const double* leg_wq;
     int nq;
+    // table encodings (data-driven / time-dependent bases, encode_table.cu): genc holds one [G][d] block of grid states
+    // per chain position (genc_stride = G*d, or 0 when every site shares one table / for the built-in bases); known and
+    // imputed values are encoded on the fly with the tables of their site (site = position, mirrored when `mirror`)
+    int64_t genc_stride;
+    int tab_kind, tab_nsites, mirror;
+    int64_t tab_istride, tab_dstride;
+    const int* tab_ip;
+    const double* tab_dp;
 };
 
 __device__ __forceinline__ void encode_any(int basis, double x, int d, double* v) {
     if (basis == MPST_BASIS_LEGENDRE_NO_NORM) encode_point<MPST_BASIS_LEGENDRE_NO_NORM>(x, d, v);
     else if (basis == MPST_BASIS_LEGENDRE_NORM) encode_point<MPST_BASIS_LEGENDRE_NORM>(x, d, v);
     else encode_point<MPST_BASIS_UNIFORM>(x, d, v);
+}
+// state of value x at chain position j (TAB: a table encoding; the built-in instantiation carries none of that code)
+template <bool TAB>
+__device__ __forceinline__ void state_at(const ImpParams& P, int j, double x, double* v) {
+    if (TAB) {
+        const int site = P.tab_nsites == 1 ? 0 : (P.mirror ? P.T - 1 - j : j);
+        table_point(P.tab_kind, x, P.d, P.tab_ip + (size_t)site * P.tab_istride, P.tab_dp + (size_t)site * P.tab_dstride, v);
+    } else encode_any(P.basis, x, P.d, v);
 }
 
 // C[n8 x n8] (+)= A * B  (or A * B^T when TB) on the FP64 tensor cores; all operands in shared memory with pitch
@@ -288,6 +305,7 @@ __device__ __forceinline__ void stage_slice_async(double* __restrict__ As, const
 }
 __device__ __forceinline__ void stage_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+template <bool TAB>
 __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
     extern __shared__ double sm[];
     const int n8 = (P.chimax + 7) & ~7;
@@ -365,7 +383,7 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
         TICK();
         for (int j = T - 1; j > last; j--) {
             const int cl = P.chi[j], cr = P.chi[j + 1];
-            if (tid == 0) encode_any(P.basis, x[j], d, phi);
+            if (tid == 0) state_at<TAB>(P, j, x[j], phi);
             const double* A = P.cores + P.core_off[j];           // [s][a][b]
             __syncthreads();
             // r'[a] = sum_s phi_s sum_b A_s[a][b] r[b]: one row a per warp at a time, lanes along b (coalesced reads
@@ -435,7 +453,7 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                     }
                 }
             } else {
-                if (tid == 0) encode_any(P.basis, x[j], d, phi);
+                if (tid == 0) state_at<TAB>(P, j, x[j], phi);
                 for (int e = tid; e < n8 * n8; e += NT) Gn[(e / n8) * ld + (e % n8)] = 0.0;   // M accumulates in Gn
                 for (int s = 0; s < d; s++) {
                     __syncthreads();
@@ -479,7 +497,7 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                 const double* A = P.cores + P.core_off[j];
                 TICK();
                 if (!mk[j]) {
-                    if (tid == 0) encode_any(P.basis, x[j], d, phi);
+                    if (tid == 0) state_at<TAB>(P, j, x[j], phi);
                     __syncthreads();
                     // v'[b] = sum_s phi_s sum_a v[a] A_s[a][b]: every core element is used once, so it is read straight
                     // from global memory (coalesced over b, loads batched); the 4 thread groups take the slices s = g mod 4
@@ -532,7 +550,7 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                     // pdf on the grid: p[g] = || rho Phi_g ||^2   (thread-contiguous chunks for the scan)
                     const int per = (G + NT - 1) / NT;
                     const int g0 = tid * per, g1 = min(G, g0 + per);
-                    if (P.basis == MPST_BASIS_LEGENDRE_NO_NORM || P.basis == MPST_BASIS_LEGENDRE_NORM) {
+                    if (!TAB && (P.basis == MPST_BASIS_LEGENDRE_NO_NORM || P.basis == MPST_BASIS_LEGENDRE_NORM)) {
                         // R = rho * diag(sqrt((2l+1)/2)), zero padded to the next supported order (in scr/rho2 space)
                         const int D = d <= 8 ? 8 : d <= 16 ? 16 : d <= 24 ? 24 : 32;
                         double* Rm = pdfR;
@@ -571,7 +589,8 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                     } else {
                         for (int g = g0; g < g1; g++) {
                             double ph[MPST_MAX_D];
-                            encode_any(P.basis, P.grid[g], d, ph);
+                            if (TAB) { for (int t2 = 0; t2 < d; t2++) ph[t2] = P.genc[(size_t)j * P.genc_stride + (size_t)g * d + t2]; }
+                            else encode_any(P.basis, P.grid[g], d, ph);
                             double pv = 0.0;
                             for (int s = 0; s < d; s++) {
                                 double t = 0.0;
@@ -728,8 +747,8 @@ __global__ void __launch_bounds__(NT, 1) impute_kernel(ImpParams P) {
                         if (P.err) P.err[(inst * P.ntraj + tr) * T + j] = errv;
                     }
                     // state of the chosen value, then v <- state . A_d
-                    if (gsel >= 0) { for (int s = tid; s < d; s += NT) phi[s] = P.genc[(size_t)gsel * d + s]; }
-                    else if (tid == 0) encode_any(P.basis, xsel, d, phi);
+                    if (gsel >= 0) { for (int s = tid; s < d; s += NT) phi[s] = P.genc[(TAB ? (size_t)j * P.genc_stride : (size_t)0) + (size_t)gsel * d + s]; }
+                    else if (tid == 0) state_at<TAB>(P, j, xsel, phi);
                     __syncthreads();
                     for (int b = tid; b < cr; b += NT) {
                         double t = 0.0;
@@ -781,7 +800,13 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     if (class_idx < 0 || class_idx >= c->C) { c->err = "impute_batch: class index out of range"; return MPST_E_INVALID; }
     if (method < MPST_IMPUTE_MEDIAN || method > MPST_IMPUTE_ITS) { c->err = "impute_batch: unknown method"; return MPST_E_INVALID; }
     if (method == MPST_IMPUTE_ITS && !uniforms) { c->err = "impute_batch: ITS needs the uniform draws"; return MPST_E_INVALID; }
-    if (c->have_phi || (c->basis != MPST_BASIS_LEGENDRE_NO_NORM && c->basis != MPST_BASIS_LEGENDRE_NORM && c->basis != MPST_BASIS_UNIFORM)) {
+    // table encodings (projected Legendre, SL / SLTD, split bases): per-site grid states, values encoded with their site's table
+    const bool tab = c->basis >= MPST_BASIS_TABLE_LEGENDRE_PROJ && c->basis <= MPST_BASIS_TABLE_SPLIT;
+    if (tab && (c->enc.kind != c->basis || c->enc.d != c->d || !c->enc.ip || !c->enc.dp || (c->enc.nsites != 1 && c->enc.nsites != c->T))) {
+        c->err = "impute_batch: no coefficient table set for this encoding (mpst_set_encoding_table)";
+        return MPST_E_INVALID;
+    }
+    if (c->have_phi || (!tab && c->basis != MPST_BASIS_LEGENDRE_NO_NORM && c->basis != MPST_BASIS_LEGENDRE_NORM && c->basis != MPST_BASIS_UNIFORM)) {
         c->err = "impute_batch: needs one of the on-device real bases";
         return MPST_E_UNSUPPORTED;
     }
@@ -860,7 +885,8 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     IMP_TRY(reserve(1, sizeof(double) * n * T, (void**)&dX));
     IMP_TRY(reserve(2, (size_t)n * T, (void**)&dmask));
     IMP_TRY(reserve(3, sizeof(double) * G, (void**)&dgrid));
-    IMP_TRY(reserve(4, sizeof(double) * (size_t)G * d, (void**)&dgenc));
+    const bool per_site = tab && c->enc.nsites != 1;                // one block of grid states per chain position
+    IMP_TRY(reserve(4, sizeof(double) * (size_t)G * d * (per_site ? T : 1), (void**)&dgenc));
     IMP_TRY(reserve(5, sizeof(double) * n * n_traj * T, (void**)&dout));
     IMP_TRY(reserve(6, sizeof(double) * ((size_t)grid * Kmax * chimax * chimax + 64), (void**)&dGR));
     IMP_TRY(reserve(7, sizeof(double) * (size_t)grid * G, (void**)&dp));
@@ -890,7 +916,10 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
         slice_core_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(v, d, chi[p], chi[p + 1], k.has_label ? class_idx : 0, dcores + off[p]);
         c->launches++;
     }
-    rc = launch_encode(c, c->basis, d, dgrid, G, dgenc, d);       // grid states, imputation.jl:92-107
+    // grid states, imputation.jl:92-107 (time-dependent encodings: one set per site, in chain order)
+    if (per_site) {
+        for (int p = 0; p < T && rc == MPST_OK; p++) rc = launch_encode_site(c, pos(p), dgrid, G, dgenc + (size_t)p * G * d, d);
+    } else rc = launch_encode_site(c, 0, dgrid, G, dgenc, d);
     if (rc != MPST_OK) { cleanup(); return rc; }
     ImpParams P;
     P.cores = dcores; P.core_off = doff; P.chi = dchi; P.X = dX; P.mask = dmask; P.grid = dgrid; P.genc = dgenc;
@@ -900,6 +929,9 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
     P.err = derr; P.get_err = (io && io->get_err) ? 1 : 0; P.max_trials = io ? io->max_trials : 0;
     P.rej_thr = rejection ? io->rejection_threshold : -1.0; P.ustride = ustride;
     P.debug = c->flag[F_IMPUTE_DEBUG] ? 1 : 0;
+    P.genc_stride = per_site ? (int64_t)G * d : 0;
+    P.tab_kind = tab ? c->enc.kind : 0; P.tab_nsites = tab ? c->enc.nsites : 1; P.mirror = backwards ? 1 : 0;
+    P.tab_istride = c->enc.istride; P.tab_dstride = c->enc.dstride; P.tab_ip = c->enc.ip; P.tab_dp = c->enc.dp;
     P.dbuf = dbuf ? 1 : 0;
     {
         double ha[MPST_MAX_D], hb[MPST_MAX_D];
@@ -934,10 +966,12 @@ int impute_batch(mpst_ctx* c, int class_idx, const double* X, const uint8_t* mis
         IMP_TRY(cudaStreamSynchronize(c->stream));                 // tab is a local temporary
         P.leg_pq = dtab; P.leg_wq = dtab + (size_t)d * nq; P.nq = nq;
     }
-    IMP_TRY(cudaFuncSetAttribute(impute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IMP_TRY(cudaFuncSetAttribute(impute_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IMP_TRY(cudaFuncSetAttribute(impute_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const auto t_setup = std::chrono::steady_clock::now();
     prof_begin(c, MPST_T_IMPUTE);
-    impute_kernel<<<grid, NT, smem, c->stream>>>(P);
+    if (tab) impute_kernel<true><<<grid, NT, smem, c->stream>>>(P);
+    else impute_kernel<false><<<grid, NT, smem, c->stream>>>(P);
     prof_end(c, MPST_T_IMPUTE);
     c->launches++;
     IMP_TRY(cudaGetLastError());

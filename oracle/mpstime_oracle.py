@@ -867,7 +867,12 @@ def impute_series_ex(class_cores, x_scaled, missing, grid, grid_enc, d, basis="l
     missing = sorted(int(m) for m in missing)
     x_out = np.array(x_scaled, dtype=np.float64).copy()
     errs = np.zeros(T)
-    phi_ts = encode(x_out, d, basis)
+    # data-driven / time-dependent encodings (imputation.jl:92-100: xvals_enc[site]): `basis` is then a callable
+    # basis(site, x) -> (..., d) and `grid_enc` holds one (G, d) block per site
+    site_enc = callable(basis)
+    grid_enc_all = np.asarray(grid_enc)
+    enc1 = (lambda j, xv: np.asarray(basis(j, np.asarray(xv, dtype=np.float64))).reshape(-1)) if site_enc else None
+    phi_ts = np.stack([enc1(j, x_out[j]) for j in range(T)]) if site_enc else encode(x_out, d, basis)
     cond = precondition(class_cores, phi_ts, missing)
     K = len(missing)
     fwd = impute_order == "forwards"
@@ -888,6 +893,7 @@ def impute_series_ex(class_cores, x_scaled, missing, grid, grid_enc, d, basis="l
     ucur = 0
     for ii, k in enumerate(order):
         rdm = A @ A.conj().T                                  # :152
+        grid_enc = grid_enc_all[missing[k]] if grid_enc_all.ndim == 3 else grid_enc_all
         p = cond_probs(rdm, grid_enc)
         err = 0.0
         if method == "median":                                # sampling_utils.jl:162-199
@@ -932,7 +938,7 @@ def impute_series_ex(class_cores, x_scaled, missing, grid, grid_enc, d, basis="l
         elif method == "mean":                                # :64-101
             Z = (grid[1] - grid[0]) * (0.5 * (p[0] + p[-1]) + np.sum(p[1:-1]))
             xv = float(np.sum(grid * p) * dxm / Z)
-            st = encode(np.array(xv), d, basis) / np.sqrt(Z)
+            st = (enc1(missing[k], xv) if site_enc else encode(np.array(xv), d, basis)) / np.sqrt(Z)
             g = -1
             if get_err:
                 err = float(np.sqrt(np.sum((grid - xv) ** 2 * p) * dxm / Z))

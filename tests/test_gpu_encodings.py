@@ -118,5 +118,8 @@ def test_fit_and_classify_with_table_encodings(ctx, oracle, pkg, enc, kw):
     Xt, _ = pkg.transform_test_data(X.T, norms, opts)
     yh, am = ctx2.overlaps(X_TxN=Xt)
     assert np.array_equal(pred, np.asarray(mps.classes)[am])
-    with pytest.raises(pkg.MPSTError):
-        pkg.init_imputation_problem(mps, X, y) and pkg.MPS_impute(pkg.init_imputation_problem(mps, X, y), 0, 0, [2, 3])
+    # imputation runs with the same tables (K8 table mode; parity in tests/test_gpu_zz_impute_tables.py)
+    imp = pkg.init_imputation_problem(mps, X, y, dx=1e-3, verbosity=-1)
+    res = pkg.MPS_impute(imp, int(classes[0]), 0, [2, 3], "median")
+    ts = np.asarray(res[0])
+    assert ts.shape[-1] == T and np.isfinite(ts).all()

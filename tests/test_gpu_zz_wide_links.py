@@ -99,3 +99,44 @@ def test_slow_decay_keeps_iterating_instead_of_jacobi(ctx, oracle, d, chi, r, mi
     kept = _check(ctx, oracle, _bond_from_matrix(M, d, chi, chi, C), d, chi, chi, False)
     assert kept == chi
     assert ctx.debug_get("svd_iters") >= min_iters, ctx.debug_get("svd_iters")
+
+
+def test_teacher_forced_bonds_with_wide_links(ctx, oracle, pkg):
+    """chi_max = 96 inside a sweep (mpst_bond_step, not the stand-alone split): bonds of a device-trained chain whose
+    links are saturated at 96 take the two-pass split; loss, gradient norm, kept dimension, singular values and the new
+    two-site product equal the oracle's bond from the same state."""
+    N, T, d, chi, eta = 512, 10, 6, 96, 0.05
+    X, y = oracle.synthetic_two_class(N, T, seed=4)
+    Xs, _ = oracle.transform_train_data(X.T)
+    phi, ys, order, counts, classes = oracle.encode_dataset(Xs, y, d)
+    ctx.train_load_x(Xs[:, order], counts, d, chi)
+    ctx.set_cores(oracle.random_start_mps(T, d, 4, 2, seed=3))
+    opts = pkg.make_opts(chi_max=chi, eta=eta)
+    ctx.sweep_bonds(opts, 2 * 2 * (T - 1), restart=True, record=False)
+    seen = 0
+    for j in range(T - 2, 1, -1):
+        cs = ctx.get_cores()
+        saturated = cs[j].shape[0] == chi and cs[j + 1].shape[2] == chi
+        ctx.debug_set("svd_twopass", 0)
+        lo, gn, k = ctx.bond_step(j, True, opts)
+        if not saturated:
+            continue
+        path, two = ctx.debug_get("svd_path"), ctx.debug_get("svd_twopass")
+        L = np.ones((N, 1))
+        for q in range(j):
+            L = oracle.env_step_left(phi[:, q], L, cs[q])
+        R = np.ones((N, 1))
+        for q in range(T - 1, j + 1, -1):
+            R = oracle.env_step_right(phi[:, q], R, cs[q])
+        B, dims = oracle.flatten_bt(cs[j], cs[j + 1])
+        Bn, lo_r, gn_r = oracle.apply_update(B, L, R, phi[:, j], phi[:, j + 1], counts, eta=eta)
+        cl, cr, S = oracle.decompose_bt(Bn, dims, True, chi, 1e-10)
+        assert abs(lo - lo_r) <= 1e-9 * abs(lo_r) and abs(gn - gn_r) <= 1e-9 * gn_r
+        assert k == len(S), (j, k, len(S))
+        dl, dr = ctx.get_core(j), ctx.get_core(j + 1)
+        assert np.abs(np.einsum(EIN, dl, dr) - np.einsum(EIN, cl, cr)).max() < 1e-10
+        sig_d = np.linalg.svd(dl.transpose(0, 3, 1, 2).reshape(-1, k), compute_uv=False)
+        assert np.abs(sig_d - S).max() < 1e-10 * S.max()
+        assert path == SVD_SUBSPACE and two == 1, (j, path, two)
+        seen += 1
+    assert seen >= 1, "no chi-saturated bond was compared"
