@@ -120,6 +120,6 @@ def test_fit_and_classify_with_table_encodings(ctx, oracle, pkg, enc, kw):
     assert np.array_equal(pred, np.asarray(mps.classes)[am])
     # imputation runs with the same tables (K8 table mode; parity in tests/test_gpu_zz_impute_tables.py)
     imp = pkg.init_imputation_problem(mps, X, y, dx=1e-3, verbosity=-1)
-    res = pkg.MPS_impute(imp, int(classes[0]), 0, [2, 3], "median")
+    res = pkg.MPS_impute(imp, int(classes[0]), 0, [2, 3], "mode")
     ts = np.asarray(res[0])
     assert ts.shape[-1] == T and np.isfinite(ts).all()
