@@ -239,3 +239,35 @@ def test_weighted_median_and_backwards_imputation(oracle):
     a, ia = oracle.impute_series(cls, x, [2, 3, 4], grid, genc, d)
     b, ib, _, _ = oracle.impute_series_ex(cls, x, [2, 3, 4], grid, genc, d)
     assert np.array_equal(a, b) and np.array_equal(ia, ib)
+
+
+def test_imputation_with_per_site_encoders(oracle):
+    """impute_at! with per-site encoders (time-dependent encodings: `xvals_enc[site]`, imputation.jl:92-100).  A per-site
+    encoder that is the same built-in basis at every site must reproduce the built-in path exactly; a genuinely
+    site-dependent one (the basis mirrored x -> -x on odd sites) must equal the built-in path on the model whose odd
+    cores carry the same mirror (P_l(-x) = (-1)^l P_l(x))."""
+    N, T, d, C = 80, 8, 4, 2
+    X, y = oracle.synthetic_two_class(N, T, seed=9)
+    Xs, _ = oracle.transform_train_data(X.T)
+    phi, ys, order, counts, classes = oracle.encode_dataset(Xs, y, d)
+    cores = oracle.fit_sweeps(oracle.random_start_mps(T, d, 4, C, seed=3), phi, counts, nsweeps=2, chi_max=6, eta=0.05)
+    cls = oracle.expand_label_index(cores)[0]
+    grid = oracle.make_grid((-1.0, 1.0), 2e-3)
+    genc = oracle.encode(grid, d)
+    x = Xs[:, order][:, 3]
+    ms = [2, 3, 4, 6]
+    U = np.array([0.3, 0.6, 0.2, 0.8])
+    same = lambda j, v: oracle.encode(v, d)                                     # noqa: E731
+    sign = (-1.0) ** np.arange(d)
+    flip = lambda j, v: oracle.encode(v, d) * (sign if j % 2 else 1.0)          # noqa: E731  == encode(-v) on odd sites
+    cls_flip = [A * (sign[None, :, None] if j % 2 else 1.0) for j, A in enumerate(cls)]
+    genc_flip = np.stack([genc * (sign if j % 2 else 1.0) for j in range(T)])
+    for method in ("median", "mean", "mode", "ITS"):
+        for order_ in ("forwards", "backwards"):
+            a = oracle.impute_series_ex(cls, x, ms, grid, genc, d, method=method, uniforms=U, impute_order=order_, get_err=True)
+            b = oracle.impute_series_ex(cls, x, ms, grid, np.stack([genc] * T), d, basis=same, method=method, uniforms=U,
+                                        impute_order=order_, get_err=True)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+            c = oracle.impute_series_ex(cls_flip, x, ms, grid, genc_flip, d, basis=flip, method=method, uniforms=U,
+                                        impute_order=order_, get_err=True)
+            assert np.abs(a[0] - c[0]).max() < 1e-9 and np.abs(a[2] - c[2]).max() < 1e-9

@@ -131,7 +131,7 @@ def config_E(fp64_peak):
             del L, R, xl, xr, B, G
     return {"rows": rows, "peak_tflops": fp64_peak,
             "note": "gradient + dense forward through mpst_bond_loss_grad on host operands (kernel times from CUDA events); "
-                    "chi = 128 has no subspace path (p <= 112 < k + 32) and takes the exact Jacobi; "
+                    "chi = 128 split timings of this table predate the deflated two-pass split: see r02_configE_splits.json; "
                     "sample_bonds_per_s counts loss + gradient only (no SVD / environment update)"}
 
 
@@ -155,8 +155,51 @@ def k1_bench(hbm):
     return out
 
 
+def config_E_splits():
+    """Only the N-independent half of the micro-sweep: one truncated split per (chi, d) on the same decaying spectrum
+    config_E uses, plus a chi_max-saturating one (sigma_k = 0.97^k).  Device time from the library's own events."""
+    ctx = m.Context(0)
+    rng = np.random.default_rng(5)
+    names = {1: "gram-tall", 2: "gram-wide", 3: "subspace", 4: "jacobi-fused", 5: "jacobi"}
+    rows = []
+    for chi in (16, 32, 64, 128):
+        for d in (6, 12, 24):
+            C, n = 2, d * chi
+            U, _ = np.linalg.qr(rng.standard_normal((C * n, n)))
+            V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+            k = np.arange(n)
+            row = {"chi": chi, "d": d, "m": C * n, "n": n}
+            for tag, sv in (("knee", np.where(k < 20, 0.5 ** np.minimum(k, 20), 0.5 ** 20 * 0.995 ** np.maximum(k - 20, 0))),
+                            ("saturating", 0.97 ** k)):
+                Mx = (U * sv) @ V.T
+                Mx /= np.linalg.norm(Mx)
+                Bs = np.ascontiguousarray(Mx.reshape(chi, C, d, d, chi).transpose(1, 4, 3, 0, 2).reshape(C, -1).T)
+                ctx.bond_split(Bs, d, chi, chi, True, chi)
+                ctx.debug_set("svd_twopass", 0)
+                ctx.profile_enable(True)
+                ctx.profile_reset()
+                t0 = time.time()
+                _, _, sig = ctx.bond_split(Bs, d, chi, chi, True, chi)
+                host_ms = 1e3 * (time.time() - t0)
+                pr = ctx.profile_get()
+                ctx.profile_enable(False)
+                row[tag] = {"split_ms_host_call": host_ms, "svd_ms_device": pr["svd"][0] if "svd" in pr else None,
+                            "path": names.get(ctx.debug_get("svd_path"), "?"), "two_pass": ctx.debug_get("svd_twopass"),
+                            "iters": ctx.debug_get("svd_iters"), "chi_kept": len(sig)}
+            rows.append(row)
+            print("Esplit", json.dumps(row), file=sys.stderr, flush=True)
+    return rows
+
+
 def main():
     which = set(sys.argv[1:]) or {"A", "E", "K1"}
+    if which == {"Esplits"}:
+        res = {"config_E_splits": config_E_splits()}
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "r02_configE_splits.json"), "w") as f:
+            json.dump(res, f, indent=1)
+        print(json.dumps(res))
+        return
     fp64 = measure_fp64_gemm_peak(0)
     hbm = measured_hbm_peak()
     res = {"fp64_gemm_peak_tflops": fp64[0], "fp64_peak_source": fp64[1], "hbm_peak_GBps": hbm[0], "hbm_peak_source": hbm[1]}
