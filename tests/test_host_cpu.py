@@ -276,3 +276,28 @@ def test_normalize_matches_direct_contraction(pkg):
         assert abs(float(E[0, 0, :].sum()) - 1.0) < 1e-12
         ratio = out[0].ravel()[0] / cores[0].ravel()[0]
         assert all(np.allclose(o, c * ratio, rtol=1e-13, atol=0) for o, c in zip(out, cores))
+
+
+@pytest.mark.parametrize("knee,r1,r2,rank,expect", [(0, 0.95, 0.95, None, 128), (0, 0.9, 0.9, None, None), (30, 0.6, 0.99, None, None),
+                                                    (0, 0.9, 0.9, 64, 64), (0, 0.9, 0.9, 70, 70)])
+def test_two_pass_split_model_equals_lapack(knee, r1, r2, rank, expect):
+    """The algorithm behind chi_max > 80 on the device (numpy model, tests/svd_two_pass_model.py): kept dimension as
+    LAPACK + truncate!, sigma / product to rounding, V orthonormal; pass 2's residuals need sigma_1^2 of the whole
+    matrix as their yardstick.  The CUDA implementation is compared with the oracle in tests/test_gpu_zz_wide_links.py."""
+    import svd_two_pass_model as tp
+    rng = np.random.default_rng(7)
+    m, n = 768, 384
+    r = rank or n
+    U, _ = np.linalg.qr(rng.standard_normal((m, r)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, r)))
+    k = np.arange(r)
+    s = np.where(k < knee, r1 ** np.minimum(k, knee), r1 ** knee * r2 ** np.maximum(k - knee, 0))
+    M = (U * s) @ V.T
+    M /= np.linalg.norm(M)
+    kl, sl, prod = tp.lapack_truncated(M, 128, 1e-10)
+    out = tp.two_pass_split(M, 128, 1e-10, rng)
+    assert out is not None
+    c, US, Vk, P = out
+    assert c == kl and (expect is None or c == expect)
+    assert np.abs(np.sqrt(P) - sl).max() < 1e-12 and np.abs(US @ Vk.T - prod).max() < 1e-12
+    assert np.abs(Vk.T @ Vk - np.eye(c)).max() < 1e-9
