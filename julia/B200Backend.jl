@@ -405,11 +405,18 @@ function get_predictions_batch(imp::ImputationProblem, class, instances::Abstrac
                                max_jump=nothing, get_wmad::Bool=false, get_std::Bool=false, rejection_threshold=:none, max_trials::Integer=10)
     impute_order in (:forwards, :backwards) || throw(ArgumentError("impute_order must be either \":forwards\" or \":backwards\""))
     haskey(METHOD_IDS, method) || error("Invalid method. Choose :mean, :mode, :median or :ITS")
-    imp.opts.encoding.istimedependent && throw(ArgumentError("B200 backend: K8 needs a data-independent real basis"))
     c = context()
     mps = imp.mpss[imp.class_map[class]]                                   # label-free class MPS (utils.jl:356-370)
     T = length(mps); d = imp.opts.d
-    model_init(c, T, 1, d, maxlinkdim(mps), BASIS_IDS[replace(imp.opts.encoding.name, "_No_Norm" => "")])
+    if imp.opts.encoding.isdatadriven || imp.opts.encoding.istimedependent
+        # K8 table mode: per-site grid states (`xvals_enc[site]`, imputation.jl:92-100) and per-site encoding of the known /
+        # imputed values are evaluated on the device from the tables built out of the reference's own `enc_args`
+        kind, ns, ip, dp = encoding_table(imp.opts, imp.enc_args, T)
+        set_encoding_table(c, kind, ns, d, ip, dp)
+        model_init(c, T, 1, d, maxlinkdim(mps), kind)
+    else
+        model_init(c, T, 1, d, maxlinkdim(mps), BASIS_IDS[replace(imp.opts.encoding.name, "_No_Norm" => "")])
+    end
     sites = get_siteinds(mps)
     for j in 1:T
         data, cl, cr, _ = dense_core(mps, j, sites, nothing)
