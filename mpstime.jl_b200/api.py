@@ -360,7 +360,7 @@ def init_imputation_problem(mps: TrainedMPS, X_test, y_test=None, dx=1e-4, guess
 def get_predictions_batch(imp: ImputationProblem, cls, instances, missing_sites_list, method="median",
                           invert_transform=True, rseed=1, num_trajectories=1, max_jump=None, uniforms=None,
                           device=None, impute_order="forwards", get_wmad=False, get_std=False,
-                          rejection_threshold=None, max_trials=10, return_err=False):
+                          rejection_threshold=None, max_trials=10, return_err=False, distributed=False):
     """Batched get_predictions (imputation.jl:264-410): instances are indices into the test series of
     class `cls`; missing_sites_list[k] are the 0-based sites to impute in instance k.  Keyword arguments are those of
     impute_median / impute_mean / impute_mode / impute_ITS (MPS_methods.jl:201-347); `rejection_threshold=None` is the
@@ -369,13 +369,33 @@ def get_predictions_batch(imp: ImputationProblem, cls, instances, missing_sites_
     like the reference does (:337-384: add the series, invert, subtract; values the logit cannot invert become NaN)."""
     if method not in ("median", "mean", "mode", "ITS"):
         raise ValueError("Invalid method. Choose :mean, :mode, :median or :ITS")
+    if distributed and _dist.rank_world()[1] > 1:
+        # one process per GPU: every rank imputes its own contiguous block of instances (no communication on the data
+        # path), then the results are concatenated in rank order on every rank
+        rank, world = _dist.rank_world()
+        b, e = _dist.shard_instances(len(instances), rank, world)
+        if uniforms is None and method == "ITS":
+            # draw the whole batch's stream on every rank so that the result does not depend on the number of ranks
+            Kmax_all = max((len(ms) for ms in missing_sites_list), default=0)
+            per_site = max_trials if rejection_threshold is not None else 1
+            uniforms = np.random.RandomState(rseed).random_sample((len(instances), num_trajectories, Kmax_all * per_site))
+        local = get_predictions_batch(imp, cls, list(instances)[b:e], list(missing_sites_list)[b:e], method=method,
+                                      invert_transform=invert_transform, rseed=rseed, num_trajectories=num_trajectories,
+                                      max_jump=max_jump, uniforms=None if uniforms is None else np.asarray(uniforms)[b:e],
+                                      device=device, impute_order=impute_order, get_wmad=get_wmad, get_std=get_std,
+                                      rejection_threshold=rejection_threshold, max_trials=max_trials, return_err=return_err)
+        return _dist.gather_instances(tuple(local))
     ctx = _context(device)
     _load_model(ctx, imp.mps)
     opts = imp.opts
     cl_inds = np.nonzero(imp.y_test == cls)[0]
     n = len(instances)
     T = imp.X_test.shape[1]
-    raw = imp.X_test[cl_inds[np.asarray(instances)]]                       # (n, T)
+    if n == 0:                                                             # an empty block of a sharded batch
+        nt = num_trajectories if method == "ITS" else 1
+        z = np.zeros((0, nt, T))
+        return (z, z.copy(), np.zeros((0, T))) if return_err else (z, np.zeros((0, T)))
+    raw = imp.X_test[cl_inds[np.asarray(instances, dtype=np.int64)]]       # (n, T)
     filled = raw.copy()
     mask = np.zeros((n, T), dtype=np.uint8)
     for k, ms in enumerate(missing_sites_list):
@@ -389,6 +409,9 @@ def get_predictions_batch(imp: ImputationProblem, cls, instances, missing_sites_
         rs = np.random.RandomState(rseed)
         per_site = max_trials if rejection_threshold is not None else 1
         uniforms = rs.random_sample((n, num_trajectories, Kmax * per_site))
+    if method == "ITS" and rejection_threshold is None:
+        # plain ITS reads uniforms[i, trajectory, k] for the k-th missing site: a wider array (drawn for a larger batch) is cut
+        uniforms = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64).reshape(n, num_trajectories, -1)[:, :, :Kmax])
     get_err = (method == "median" and get_wmad) or (method == "mean" and get_std)
     out, err = ctx.impute_batch(imp.class_map[cls], Xs, mask.T, imp.xvals, method=method, uniforms=uniforms,
                                 n_traj=num_trajectories if method == "ITS" else 1,

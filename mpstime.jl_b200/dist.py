@@ -45,3 +45,23 @@ def init_comm(ctx):
     td.broadcast_object_list(box, src=0)
     ctx.comm_init(box[0], rank, world)
     return rank, world
+
+
+def shard_instances(n, rank, world):
+    """Imputation / classification shard by instance with no data-path collective: rank r takes the
+    contiguous block [n r / world, n (r + 1) / world)."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def gather_instances(local):
+    """Concatenate every rank's block (leading axis = instances) in rank order on every rank: host-language plumbing
+    (torch.distributed object all-gather), results only -- the series, masks and cores never cross ranks."""
+    rank, world = rank_world()
+    if world == 1:
+        return local
+    import torch.distributed as td
+    box = [None] * world
+    td.all_gather_object(box, local)
+    if isinstance(local, tuple):
+        return tuple(np.concatenate([b[k] for b in box], axis=0) for k in range(len(local)))
+    return np.concatenate(box, axis=0)

@@ -134,6 +134,13 @@ for loss in ("KLD", "MSE"):
     G = buf[:-1].numpy().reshape(G_full.shape); lo = float(buf[-1])
     assert abs(lo - lo_full) < 1e-12 * abs(lo_full), (lo, lo_full)
     assert np.abs(G - G_full).max() < 1e-12 * np.abs(G_full).max()
+# imputation / classification: contiguous instance blocks per rank, results concatenated in rank order on every rank
+n_inst = 7
+b, e = m.dist.shard_instances(n_inst, rank, world)
+full = np.arange(n_inst * 3, dtype=np.float64).reshape(n_inst, 1, 3)
+got = m.dist.gather_instances((full[b:e], 2.0 * full[b:e]))
+assert np.array_equal(got[0], full) and np.array_equal(got[1], 2.0 * full)
+assert np.array_equal(m.dist.gather_instances(full[b:e, 0]), full[:, 0])
 td.barrier()
 if rank == 0: print("GLOO_OK")
 '''
