@@ -301,10 +301,17 @@ def _load_model(ctx, mps: TrainedMPS):
     return enc, T, C
 
 
-def classify(mps: TrainedMPS, X_test, device=None):
+def classify(mps: TrainedMPS, X_test, device=None, distributed=False):
     """classify(mps, X_test) -> predicted labels (summary.jl:155-177 -> :116-136): re-derive the train
-    normalisation from mps.train_data.original_data, scale the test set with it, argmax_c |yhat_c|^2."""
+    normalisation from mps.train_data.original_data, scale the test set with it, argmax_c |yhat_c|^2.
+    `distributed`: under torch.distributed every rank classifies its contiguous block of the test series on its own
+    GPU (no data-path collective) and the labels are concatenated in rank order on every rank."""
     X_test = np.asarray(X_test, dtype=np.float64)
+    if distributed and _dist.rank_world()[1] > 1:
+        rank, world = _dist.rank_world()
+        b, e = _dist.shard_instances(X_test.shape[0], rank, world)
+        local = classify(mps, X_test[b:e], device=device) if e > b else np.asarray(mps.classes)[:0]
+        return _dist.gather_instances(np.asarray(local))
     ctx = _context(device)
     _load_model(ctx, mps)
     _, norms = transform_train_data(mps.train_data.original_data.T, mps.opts)     # :159-160
