@@ -49,6 +49,21 @@ rec2 = []
 o.fit_sweeps(cores, phi, counts, nsweeps=1, chi_max=10, eta=0.05, record=rec2, max_bonds=4)
 for k in range(4):
     assert abs(lo2[k] - rec2[k]["loss"]) < 1e-9 * abs(rec2[k]["loss"]) and abs(gn2[k] - rec2[k]["gradnorm"]) < 1e-8 * rec2[k]["gradnorm"]
+# public API under torch.distributed: fitMPS shards the samples, classify / imputation shard by instance (no data-path
+# collective); every rank ends with the same labels / imputed series as its own unsharded call
+Xr, yr = o.synthetic_two_class(160, 10, seed=5)
+mo = m.MPSOptions(d=4, chi_max=8, nsweeps=2, eta=0.05, verbosity=-1, log_level=0)
+mps, _, _ = m.fitMPS(Xr, yr, opts=mo)
+hs = [None] * world
+td.all_gather_object(hs, hashlib.sha256(b"".join(np.ascontiguousarray(c).tobytes() for c in mps.mps)).hexdigest())
+assert len(set(hs)) == 1, hs
+assert np.array_equal(m.classify(mps, Xr, distributed=True), m.classify(mps, Xr))
+imp = m.init_imputation_problem(mps, Xr, yr, dx=1e-3, verbosity=-1)
+inst = list(range(7)); miss = [[2, 3, 4]] * 3 + [[5, 6]] * 4
+for method in ("median", "ITS"):
+    a = m.get_predictions_batch(imp, int(yr.min()), inst, miss, method=method, distributed=True, return_err=True)
+    b = m.get_predictions_batch(imp, int(yr.min()), inst, miss, method=method, return_err=True)
+    assert all(np.array_equal(x, y2, equal_nan=True) for x, y2 in zip(a, b)), method
 td.barrier()
 if rank == 0: print("MULTI_OK")
 '''
