@@ -756,6 +756,12 @@ static int subspace_core(mpst_ctx* c, const double* M, int64_t ldm, int m, int n
         if (p < k + 32 || n <= p || m < p) return MPST_OK;            // too little oversampling: full Jacobi
     }
     if (c->svd_prepare_only && mode != 2) return MPST_OK;              // only the subspace rounds are graphs
+    // Gram paths: the Gram matrix goes through the same Cholesky + register-resident Jacobi as the Rayleigh-Ritz step of
+    // the subspace path (order rounded up to a multiple of 16, zero padded: the padding columns are deflated by the
+    // Cholesky and come out as Ritz value 0, ranked last) instead of the shared-memory Jacobi on the columns of H
+    // (2.2 ms at order 96); MPST_SVD_GRAMSMEM=1 restores that solver
+    const bool gram_reg = mode != 2 && !c->flag[F_SVD_GRAMSMEM];
+    if (gram_reg) p = std::max(32, (int)round_up(mode == 0 ? n : m, 16));
     const size_t need = (size_t)2 * n * p + (size_t)2 * m * p + (size_t)(MAXSPLIT + 4) * p * p + (size_t)2 * n * k +
                         (size_t)m * k + 4 * p + 64;
     TRY(ensure_buf(c, &c->sub, &c->subcap, need));
@@ -820,9 +826,19 @@ static int subspace_core(mpst_ctx* c, const double* M, int64_t ldm, int m, int n
         // ---- Gram paths: one small symmetric eigenproblem, no iteration ----
         const int q = mode == 0 ? n : m;                               // order of H (p = q rounded up to even)
         int splits = 1;
+        if (gram_reg) {
+            CUDA_TRY(c, cudaMemsetAsync(Gm, 0, sizeof(double) * (size_t)p * p, c->stream));
+            if (mode == 0) TRY(launch_dgemm(c, 1, 0, q, q, m, M, ldm, M, ldm, Gm, p));                      // M^T M, ld = p
+            else TRY(launch_dgemm(c, 0, 1, q, q, n, M, ldm, M, ldm, Gm, p));                               // M M^T
+            launch_chol_inv(p, Gm, 1, Ri, Lm, status, c->stream, !c->flag[F_SVD_CHOLSEQ]);                 // H = L L^T
+            c->launches++;
+            if (!launch_sym_eig_reg(p, Lm, Wm, ev, status, c->stream))
+                if (launch_sym_eig<true>(p, eig_smem, Lm, 1, p, Wm, ev, status, c->stream)) CUDA_TRY(c, cudaGetLastError());
+        } else {
         if (mode == 0) TRY(launch_dgemm_splitk(c, 1, 0, q, q, m, M, ldm, M, ldm, Gm, MAXSPLIT, &splits));   // M^T M
         else TRY(launch_dgemm_splitk(c, 0, 1, q, q, n, M, ldm, M, ldm, Gm, MAXSPLIT, &splits));            // M M^T
         if (launch_sym_eig<false>(p, eig_smem, Gm, splits, q, Wm, ev, status, c->stream)) CUDA_TRY(c, cudaGetLastError());
+        }
         ritz_trunc_kernel<<<1, 256, 0, c->stream>>>(ev, p, q, trace_dev, chi_max, cutoff, c->perm, ev + p, c->iscal);
         gather_cols_kernel<<<(p * k + 255) / 256, 256, 0, c->stream>>>(Wm, p, c->perm, k, Wk);
         c->launches += 3;
