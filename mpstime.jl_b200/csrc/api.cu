@@ -218,7 +218,7 @@ const FlagDef kFlags[F_COUNT] = {
     {"SVD_PB64", 0, true}, {"SVD_LEGACY", 0, true}, {"SVD_NOSUB", 0, true}, {"SVD_OVS", 0, false},
     {"SVD_NOHALF", 0, true}, {"SVD_HALF_FROM", 1, false}, {"SVD_IT", 0, false}, {"SVD_NOGRAPH", 0, true},
     {"GRAD_KC", 0, false}, {"IMPUTE_NOSERIES", 0, true}, {"IMPUTE_FULLSYM", 0, true}, {"GRAD_PHASES", 0, false},
-    {"SVD_EIGSMEM", 0, true}, {"SVD_SERIAL", 0, true}, {"SVD_CHOLSEQ", 0, true}, {"SVD_PROBE", 0, true}, {"SVD_SYNCFIRST", 0, true}, {"SVD_NOPREP", 0, true}, {"KRAO_NOSLAB", 0, true}, {"KRAO_SLAB_MI", 0, false}, {"KRAO_SLAB_MIN", 25, false}, {"SVD_FIRST", 7, false}, {"SVD_NO2PASS", 0, true}, {"SVD_GRAMSMEM", 0, true},
+    {"SVD_EIGSMEM", 0, true}, {"SVD_SERIAL", 0, true}, {"SVD_CHOLSEQ", 0, true}, {"SVD_PROBE", 0, true}, {"SVD_SYNCFIRST", 0, true}, {"SVD_NOPREP", 0, true}, {"KRAO_NOSLAB", 0, true}, {"KRAO_SLAB_MI", 0, false}, {"KRAO_SLAB_MIN", 25, false}, {"SVD_FIRST", 7, false}, {"SVD_NO2PASS", 0, true}, {"SVD_GRAMREG", 0, true},
 };
 const char* kLast[L_COUNT] = {"svd_path", "svd_iters", "svd_restarts", "grad_kernel", "grad_variant", "krao_kernel",
                               "krao_variant", "fwd_path", "krao_reg_mask", "grad_kr_launches", "grad_tile_launches", "svd_calls",

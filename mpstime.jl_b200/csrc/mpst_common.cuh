@@ -45,7 +45,7 @@ struct Timer {
 enum {
     F_DENSE_FWD = 0, F_NO_ENV_REUSE, F_GRAD_T128, F_GRAD_NOKR, F_IMPUTE_NODBUF, F_IMPUTE_DEBUG, F_KRAO_NOREG,
     F_SVD_INNER, F_SVD_DEBUG, F_SVD_SKIP, F_SVD_FIXED, F_SVD_FULL, F_SVD_PB64, F_SVD_LEGACY, F_SVD_NOSUB, F_SVD_OVS,
-    F_SVD_NOHALF, F_SVD_HALF_FROM, F_SVD_IT, F_SVD_NOGRAPH, F_GRAD_KC, F_IMPUTE_NOSERIES, F_IMPUTE_FULLSYM, F_GRAD_PHASES, F_SVD_EIGSMEM, F_SVD_SERIAL, F_SVD_CHOLSEQ, F_SVD_PROBE, F_SVD_SYNCFIRST, F_SVD_NOPREP, F_KRAO_NOSLAB, F_KRAO_SLAB_MI, F_KRAO_SLAB_MIN, F_SVD_FIRST, F_SVD_NO2PASS, F_SVD_GRAMSMEM, F_COUNT
+    F_SVD_NOHALF, F_SVD_HALF_FROM, F_SVD_IT, F_SVD_NOGRAPH, F_GRAD_KC, F_IMPUTE_NOSERIES, F_IMPUTE_FULLSYM, F_GRAD_PHASES, F_SVD_EIGSMEM, F_SVD_SERIAL, F_SVD_CHOLSEQ, F_SVD_PROBE, F_SVD_SYNCFIRST, F_SVD_NOPREP, F_KRAO_NOSLAB, F_KRAO_SLAB_MI, F_KRAO_SLAB_MIN, F_SVD_FIRST, F_SVD_NO2PASS, F_SVD_GRAMREG, F_COUNT
 };
 // which code path the last call took (mpst_debug_get): lets the parity tests assert that they exercised the
 // kernels the benchmark runs, and lets bench.py name the kernel it reports a roofline for

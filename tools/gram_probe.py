@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Device time of the Gram-path splits (d * chi <= 112 columns): Cholesky + register-resident Jacobi (default) against
-the shared-memory Jacobi on the columns of H (MPST_SVD_GRAMSMEM)."""
+"""Device time of the Gram-path splits (d * chi <= 112 columns): Cholesky + register-resident Jacobi (opt-in, MPST_SVD_GRAMREG) against
+the default shared-memory Jacobi on the columns of H."""
 import json
 import os
 import sys
@@ -23,7 +23,7 @@ for d, chi in ((6, 16), (10, 10), (5, 20), (2, 15), (4, 8)):
     row = {"d": d, "chi": chi, "m": C * n, "n": n}
     outs = {}
     for name, flag in (("chol_reg", 0), ("smem", 1)):
-        ctx.debug_set("SVD_GRAMSMEM", flag)
+        ctx.debug_set("SVD_GRAMREG", 1 - flag)
         ctx.bond_split(B, d, chi, chi, True, chi)
         ctx.profile_enable(True)
         ctx.profile_reset()
@@ -32,7 +32,7 @@ for d, chi in ((6, 16), (10, 10), (5, 20), (2, 15), (4, 8)):
         row[name + "_svd_ms_device"] = ctx.profile_get()["svd"][0] / 5
         row[name + "_path"] = ctx.debug_get("svd_path")
         ctx.profile_enable(False)
-    ctx.debug_set("SVD_GRAMSMEM", 0)
+    ctx.debug_set("SVD_GRAMREG", 0)
     a, b = outs["chol_reg"], outs["smem"]
     row["kept"] = (len(a[2]), len(b[2]))
     row["sigma_diff"] = float(np.abs(a[2] - b[2]).max()) if len(a[2]) == len(b[2]) else None
