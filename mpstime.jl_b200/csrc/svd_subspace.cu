@@ -760,9 +760,10 @@ static int subspace_core(mpst_ctx* c, const double* M, int64_t ldm, int m, int n
     // Jacobi as the Rayleigh-Ritz step of the subspace path (order rounded up to a multiple of 16, zero padded) instead of
     // the shared-memory Jacobi on the columns of H.  5x faster at order 96 and identical on full-rank bonds, but NOT the
     // default: on a numerically rank-deficient H (first-sweep bonds of a small training set: 20-28 of 80 pivots at
-    // rounding level) a noise pivot that slips past the relative deflation test yields a garbage column of L, and the
-    // Gram paths have no residual check to catch it (teacher-forced A/B on the 67-sample reference case: truncated
-    // products 5e-4 apart, test accuracy after one sweep 0.918 against 0.972 / 0.973 for the oracle / the default).
+    // rounding level) deflating a pivot d_k drops that column's off-diagonal entries, which are sqrt(d_k h_jj)-sized
+    // (an un-pivoted Cholesky of a semi-definite matrix), and the Gram paths have no residual check to catch it
+    // (teacher-forced A/B on the 67-sample reference case: truncated products 5e-4 apart, test accuracy after one
+    // sweep 0.918 against 0.972 / 0.973 for the oracle / the default).
     const bool gram_reg = mode != 2 && c->flag[F_SVD_GRAMREG];
     if (gram_reg) p = std::max(32, (int)round_up(mode == 0 ? n : m, 16));
     const size_t need = (size_t)2 * n * p + (size_t)2 * m * p + (size_t)(MAXSPLIT + 4) * p * p + (size_t)2 * n * k +
