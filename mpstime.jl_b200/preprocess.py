@@ -93,19 +93,19 @@ def transform_test_data(X, norms, opts, rescale_out_of_bounds=True):
         Xs = Xs * (ub - lb) + lb
     oob = []
     if rescale_out_of_bounds:
-        for i in range(Xs.shape[1]):
-            col = Xs[:, i]
-            lb_s, ub_s = 0.0, 1.0
-            lo, hi = col.min(), col.max()
-            if lo < 0:
-                col -= lo
-                hi = col.max()
-                lb_s = float(lo)
-            if hi > 1:
-                col /= hi
-                ub_s = float(hi)
-            if (lb_s, ub_s) != (0.0, 1.0):
-                oob.append((i, lb_s, ub_s))
+        # per series (utils.jl:236-262): shift up when the minimum is below 0, then divide when the maximum is above 1;
+        # all series at once -- the same element-wise operations as the per-column loop, so the same bits
+        Xs = np.ascontiguousarray(Xs)
+        lo = Xs.min(axis=0)
+        low = lo < 0
+        if low.any():
+            Xs[:, low] -= lo[low]
+        hi = Xs.max(axis=0)
+        high = hi > 1
+        if high.any():
+            Xs[:, high] /= hi[high]
+        for i in np.nonzero(low | high)[0]:
+            oob.append((int(i), float(lo[i]) if low[i] else 0.0, float(hi[i]) if high[i] else 1.0))
     a, b = encoding_range(opts.encoding)
     Xs = (b - a) * Xs + a
     return (Xs[:, 0] if single else Xs), oob
