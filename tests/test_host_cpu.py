@@ -308,3 +308,37 @@ def test_two_pass_split_model_equals_lapack(knee, r1, r2, rank, expect):
     assert c == kl and (expect is None or c == expect)
     assert np.abs(np.sqrt(P) - sl).max() < 1e-12 and np.abs(US @ Vk.T - prod).max() < 1e-12
     assert np.abs(Vk.T @ Vk - np.eye(c)).max() < 1e-9
+
+
+def test_out_of_bounds_rescale_equals_the_per_series_loop(pkg):
+    """transform_test_data (utils.jl:202-278): the vectorised out-of-bounds rescale is the reference's per-series loop
+    (shift up when the minimum is below 0, then divide when the maximum is above 1), bit for bit, and
+    invert_test_transform undoes it."""
+    rng = np.random.default_rng(0)
+    opts = pkg.MPSOptions(d=4, chi_max=8)
+    Xtr = rng.standard_normal((200, 30)).cumsum(1)
+    _, norms = pkg.transform_train_data(Xtr.T, opts)
+    Xte = rng.standard_normal((500, 30)).cumsum(1) * 1.4 + 0.3
+    got, oob = pkg.transform_test_data(Xte.T, norms, opts)
+    ref = norms.apply(Xte.T)
+    want_oob = []
+    for i in range(ref.shape[1]):                     # the literal loop
+        col = ref[:, i]
+        lb_s, ub_s = 0.0, 1.0
+        lo, hi = col.min(), col.max()
+        if lo < 0:
+            col -= lo
+            hi = col.max()
+            lb_s = float(lo)
+        if hi > 1:
+            col /= hi
+            ub_s = float(hi)
+        if (lb_s, ub_s) != (0.0, 1.0):
+            want_oob.append((i, lb_s, ub_s))
+    a, b = pkg.api.encoding_range(opts.encoding)
+    assert np.array_equal(got, (b - a) * ref + a) and oob == want_oob and len(oob) > 10
+    assert got.min() >= a and got.max() <= b
+    back = pkg.invert_test_transform(got, oob, norms, opts)
+    assert np.abs(back - Xte.T).max() < 1e-6 * np.abs(Xte).max()
+    one, oob1 = pkg.transform_test_data(Xte[7], norms, opts)
+    assert np.array_equal(one, got[:, 7])
